@@ -1,0 +1,405 @@
+// Implicit-GEMM convolution / linear layer on Blackwell tensor cores.
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, tap, cin]
+//
+// One CTA computes a 128-pixel x BLOCK_N-channel output tile.  The 128 pixels are a tile_w x tile_h patch of
+// the NHWC output map; for every filter tap the TMA engine fetches the shifted tile_w x tile_h x 64-channel
+// box of the input straight into 128B-swizzled shared memory (out-of-bounds coordinates are zero-filled by
+// the hardware, which is the convolution's zero padding), so no im2col buffer ever exists.  A single elected
+// thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16/fp16 in, fp32 accumulate in TMEM); four epilogue
+// warps read the accumulator back with tcgen05.ld and apply bias / activation / layer-scale+residual, and
+// optionally accumulate GroupNorm statistics, before a vectorised NHWC store.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Reference call sites replaced: see include/unicorn_b200.h (uc_conv2d).
+#include "uc_ptx.cuh"
+#include "uc_common.h"
+#include "../../include/unicorn_b200.h"
+
+namespace uc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 16-bit elements -> 128-byte rows
+constexpr int kMaxTaps = 9;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+struct ConvTap {
+  int16_t map, dw, dh, tap;
+};
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  ConvTap taps[kMaxTaps];
+  int ntaps, kchunks;
+  int tile_w, tile_h, tiles_w, tiles_h;
+  int Wo, Ho, B, Cout;
+  uint32_t idesc;
+  const float* bias;
+  const float* gamma;
+  const void* res;
+  int ldres;
+  void* y;
+  int ldy, y_dtype, act;
+  float* gn_stats;
+  int gn_groups, gn_gs;  // gs = Cout / groups
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case UC_ACT_RELU: return fmaxf(x, 0.f);
+    case UC_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case UC_ACT_SILU: return x / (1.f + __expf(-x));
+    case UC_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    default: return x;
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int mt = blockIdx.y;
+  const int twi = mt % p.tiles_w;
+  const int thi = (mt / p.tiles_w) % p.tiles_h;
+  const int b = mt / (p.tiles_w * p.tiles_h);
+  const int ow0 = twi * p.tile_w, oh0 = thi * p.tile_h;
+  const int total = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[0]);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const ConvTap tp = p.taps[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
+          tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+          tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+        const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
+                   (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> fused math -> NHWC global
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int wi = row % p.tile_w, hi = row / p.tile_w;
+    const int ow = ow0 + wi, oh = oh0 + hi;
+    const bool valid = (ow < p.Wo) && (oh < p.Ho);
+    const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float gs_sum = 0.f, gs_sq = 0.f;
+    int gs_left = p.gn_gs;
+    int gs_group = p.gn_stats ? n0 / p.gn_gs : 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      if (n0 + c0 >= p.Cout) break;
+      uint32_t v[32];
+      if constexpr (BLOCK_N % 32 == 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      } else {
+        uint32_t h[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, h);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
+      }
+      tmem_ld_wait();
+      const int cbase = n0 + c0;
+      const int ncols = min(32, min(BLOCK_N - c0, p.Cout - cbase));  // multiple of 8
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+          }
+        }
+      }
+      if (p.gn_stats) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < ncols) {
+            const float x = valid ? f[j] : 0.f;
+            gs_sum += x;
+            gs_sq += x * x;
+            if (--gs_left == 0) {
+              float s = gs_sum, ss = gs_sq;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+              }
+              if (lane == 0) {
+                float* dst = p.gn_stats + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
+                atomicAdd(dst, s);
+                atomicAdd(dst + 1, ss);
+              }
+              gs_sum = 0.f; gs_sq = 0.f; gs_left = p.gn_gs; ++gs_group;
+            }
+          }
+        }
+      }
+      if (p.act != UC_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+      }
+      if (p.gamma) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
+            f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
+          }
+        }
+      }
+      if (valid) {
+        if (p.res) {
+          const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+                f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+              }
+            }
+          }
+        }
+        if (p.y_dtype == UC_F32) {
+          float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+        } else {
+          uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              uint4 o;
+              o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
+              o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
+              o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
+              o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
+              *reinterpret_cast<uint4*>(yp + j) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem);
+    if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d> launch: %s", BLOCK_N, STAGES, cudaGetErrorString(e));
+  return UC_OK;
+}
+
+static int pick_block_n(int Cout, int m_tiles, int gn_gs) {
+  static const int cands[] = {256, 192, 128, 96, 64, 32, 16};
+  int best = 0;
+  long best_cost = -1;
+  for (int bn : cands) {
+    if (gn_gs > 0 && (bn % gn_gs) != 0) continue;  // GroupNorm groups must not straddle N tiles
+    const int nt = (Cout + bn - 1) / bn;
+    const long waste_cols = static_cast<long>(nt) * bn - Cout;
+    if (waste_cols * 8 > Cout && bn > 16 && gn_gs <= 0) continue;  // > 12.5 % padded columns
+    const long ctas = static_cast<long>(nt) * m_tiles;
+    // cost model: waves over 148 SMs x per-CTA time (~ bn + fixed overhead equivalent to 48 columns)
+    const long waves = (ctas + 147) / 148;
+    const long cost = waves * (bn + 48);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace uc
+
+using namespace uc;
+
+extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!d || !d->x || !d->w || !d->y) return set_error(UC_EINVAL, "uc_conv2d: null pointer");
+  if (d->x_dtype != UC_BF16 && d->x_dtype != UC_F16) return set_error(UC_EINVAL, "uc_conv2d: x must be bf16/f16");
+  if (d->Cin % 8 || d->Cout % 8 || d->ldx % 8 || d->ldy % 8 || d->ldx < d->Cin || d->ldy < d->Cout)
+    return set_error(UC_EINVAL, "uc_conv2d: Cin/Cout/ldx/ldy must be multiples of 8 (Cin=%d Cout=%d ldx=%d ldy=%d)",
+                     d->Cin, d->Cout, d->ldx, d->ldy);
+  if (d->stride != 1 && d->stride != 2) return set_error(UC_EINVAL, "uc_conv2d: stride must be 1 or 2");
+  if (d->KH * d->KW > kMaxTaps || d->KH < 1 || d->KW < 1) return set_error(UC_EINVAL, "uc_conv2d: at most 9 taps");
+  if (d->pad < 0 || d->pad >= d->KH + 1) return set_error(UC_EINVAL, "uc_conv2d: bad pad");
+  if (d->res && (d->ldres % 8 || d->y_dtype == UC_F32)) return set_error(UC_EINVAL, "uc_conv2d: residual needs 16-bit y, ldres%%8==0");
+  if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->w) | reinterpret_cast<uintptr_t>(d->y)) & 15)
+    return set_error(UC_EINVAL, "uc_conv2d: pointers must be 16-byte aligned");
+  if (d->gn_stats && (d->gn_groups <= 0 || d->Cout % d->gn_groups || (d->Cout / d->gn_groups) % 4))
+    return set_error(UC_EINVAL, "uc_conv2d: bad GroupNorm grouping");
+  int rc = ensure_driver();
+  if (rc) return rc;
+
+  const int s = d->stride;
+  const int Ho = (d->H + 2 * d->pad - d->KH) / s + 1;
+  const int Wo = (d->W + 2 * d->pad - d->KW) / s + 1;
+  if (Ho <= 0 || Wo <= 0) return set_error(UC_EINVAL, "uc_conv2d: empty output");
+
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  const CUtensorMapDataType dt = d->x_dtype == UC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const bool flat = (d->KH == 1 && d->KW == 1 && s == 1 && d->pad == 0);
+  int B = d->B, Hm = d->H, Wm = d->W;  // map geometry
+  if (flat) { Wm = d->B * d->H * d->W; Hm = 1; B = 1; }
+  p.Wo = flat ? Wm : Wo;
+  p.Ho = flat ? 1 : Ho;
+  p.B = B;
+  // tile shape minimising the number of 128-pixel tiles
+  {
+    int best_tw = 128, best_th = 1;
+    long best = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const long n = static_cast<long>((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+      if (best < 0 || n < best) { best = n; best_tw = tw; best_th = th; }
+    }
+    p.tile_w = best_tw; p.tile_h = best_th;
+  }
+  p.tiles_w = (p.Wo + p.tile_w - 1) / p.tile_w;
+  p.tiles_h = (p.Ho + p.tile_h - 1) / p.tile_h;
+  const int m_tiles = p.tiles_w * p.tiles_h * B;
+
+  // activation maps: one per stride phase
+  const size_t es = 2;
+  for (int ph = 0; ph < s; ++ph) {
+    for (int pw = 0; pw < s; ++pw) {
+      const int Wp = (Wm - pw + s - 1) / s, Hp = (Hm - ph + s - 1) / s;
+      if (Wp <= 0 || Hp <= 0) continue;
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(d->x) + (static_cast<size_t>(ph) * Wm + pw) * d->ldx * es;
+      uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(Wp), static_cast<uint64_t>(Hp), static_cast<uint64_t>(B)};
+      uint64_t strides[3] = {static_cast<uint64_t>(s) * d->ldx * es, static_cast<uint64_t>(s) * Wm * d->ldx * es,
+                             static_cast<uint64_t>(Hm) * Wm * d->ldx * es};
+      uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+      rc = encode_tmap(&p.tmA[ph * s + pw], dt, 4, base, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
+  int nt = 0;
+  for (int kh = 0; kh < d->KH; ++kh) {
+    for (int kw = 0; kw < d->KW; ++kw) {
+      const int offh = kh - d->pad, offw = kw - d->pad;
+      const int ph = ((offh % s) + s) % s, pw = ((offw % s) + s) % s;
+      ConvTap t;
+      t.map = static_cast<int16_t>(ph * s + pw);
+      t.dh = static_cast<int16_t>((offh - ph) / s);
+      t.dw = static_cast<int16_t>((offw - pw) / s);
+      t.tap = static_cast<int16_t>(kh * d->KW + kw);
+      p.taps[nt++] = t;
+    }
+  }
+  p.ntaps = nt;
+  p.kchunks = (d->Cin + kBlockK - 1) / kBlockK;
+
+  const int gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 0;
+  const int bn = d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
+  if (bn == 0) return set_error(UC_EINVAL, "uc_conv2d: no N tile compatible with GroupNorm group size %d", gn_gs);
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(nt), static_cast<uint64_t>(d->Cout)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d->Cin) * es, static_cast<uint64_t>(nt) * d->Cin * es};
+    uint32_t box[3] = {static_cast<uint32_t>(kBlockK), 1, static_cast<uint32_t>(bn)};
+    rc = encode_tmap(&p.tmB, dt, 3, d->w, dims, strides, box);
+    if (rc) return rc;
+  }
+  p.Cout = d->Cout;
+  p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
+  p.bias = d->bias; p.gamma = d->gamma; p.res = d->res; p.ldres = d->ldres;
+  p.y = d->y; p.ldy = d->ldy; p.y_dtype = d->y_dtype; p.act = d->act;
+  p.gn_stats = d->gn_stats; p.gn_groups = d->gn_groups;
+  p.gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 1 << 30;
+  if (d->gn_stats && (bn % p.gn_gs) != 0)
+    return set_error(UC_EINVAL, "uc_conv2d: N tile %d incompatible with GroupNorm group size %d", bn, p.gn_gs);
+  if (m_tiles > 65535) return set_error(UC_EINVAL, "uc_conv2d: too many M tiles (%d)", m_tiles);
+  dim3 grid((d->Cout + bn - 1) / bn, m_tiles, 1);
+  switch (bn) {
+    case 256: return launch_conv<256, 4>(p, grid, stream);
+    case 192: return launch_conv<192, 5>(p, grid, stream);
+    case 128: return launch_conv<128, 3>(p, grid, stream);
+    case 96: return launch_conv<96, 3>(p, grid, stream);
+    case 64: return launch_conv<64, 4>(p, grid, stream);
+    case 32: return launch_conv<32, 4>(p, grid, stream);
+    case 16: return launch_conv<16, 4>(p, grid, stream);
+    default: return set_error(UC_EINVAL, "uc_conv2d: unsupported block_n %d", bn);
+  }
+}
