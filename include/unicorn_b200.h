@@ -86,6 +86,71 @@ typedef struct UcConv2d {
 } UcConv2d;
 UC_API int uc_conv2d(const UcConv2d* d, void* stream);
 
+/* ConvNeXt stem: Conv2d(3,C0,k4,s4)+bias then channels_first LayerNorm (backbone/convnext.py:77-80,179-184).
+ * img fp32 NCHW [B,3,H,W]; w48 fp32 [48][C0] with k=(ci*4+kh)*4+kw; out NHWC bf16 [B,H/4,W/4,C0]. */
+UC_API int uc_stem_ln(const float* img, const float* w48, const float* bias, const float* lnw, const float* lnb,
+                      void* out_bf16, int B, int H, int W, int C0, float eps, void* stream);
+
+/* ConvNeXt block front half: depthwise 7x7 (pad 3)+bias then LayerNorm over C (convnext.py:43-45).
+ * x,y NHWC bf16 contiguous [B,H,W,C]; w49 fp32 [49][C] (k = kh*7+kw). */
+UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias, const float* lnw, const float* lnb,
+                         void* y_bf16, int B, int H, int W, int C, float eps, void* stream);
+
+/* Row LayerNorm: y[m,:] = LN(x[m,:] + res[m,:]) * w + b  (res may be NULL).  16-bit rows with element strides.
+ * convnext.py:176-184 (downsample / out norms), deformable_transformer.py:113,121,127-130 (post-norm). */
+UC_API int uc_layernorm(const void* x, int ldx, const void* res, int ldres, const float* w, const float* b, void* y,
+                        int ldy, long M, int C, float eps, int dtype, void* stream);
+
+/* GroupNorm apply with the statistics accumulated by uc_conv2d (gn_stats = [B][G]{sum,sumsq}):
+ * y = act((x-mean)*rstd*w+b) [+ prior[pix]*beta[c]] ; optional second output y2 = y + add2.
+ * network_blocks.py:50-51 with exp/unicorn_track.py:450-470 (GN16, eps 1e-3, SiLU); unicorn.py:38 (GN32, eps 1e-5);
+ * unicorn_head.py:272-275 (prior fusion).  x,y,add2,y2 bf16 NHWC with pixel strides. */
+UC_API int uc_groupnorm_apply(const void* x, int ldx, const float* stats, const float* w, const float* b, void* y,
+                              int ldy, int B, long HW, int C, int G, float eps, int act, const float* prior,
+                              const float* beta, const void* add2, int ldadd2, void* y2, int ldy2, void* stream);
+
+/* dst[b,oh,ow,:C] = src[b,oh/up,ow/up,:C], up in {1,2} (nearest upsample + concat slice; yolo_pafpn_new.py:139-146). */
+UC_API int uc_copy_upsample(const void* src, int lds, void* dst, int ldd, int B, int Hs, int Ws, int C, int up, void* stream);
+/* nn.PixelShuffle(2) in NHWC (unicorn.py:41): in [B,H,W,4*Co] -> out [B,2H,2W,Co], 16-bit. */
+UC_API int uc_pixel_shuffle2(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co, void* stream);
+/* F.interpolate(bilinear, align_corners=False) on fp32 planes [P,Hs,Ws]->[P,Hd,Wd]; scale_* = 1/scale_factor or 0. */
+UC_API int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int Ws, int Hd, int Wd, float scale_h,
+                           float scale_w, void* stream);
+UC_API int uc_add(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long M, int C, int dtype, void* stream);
+UC_API int uc_nchw_f32_to_nhwc(const float* src, void* dst, int ldd, int B, int C, long HW, int dtype, void* stream);
+UC_API int uc_nhwc_to_nchw_f32(const void* src, int lds, float* dst, int B, int C, long HW, int dtype, void* stream);
+
+/* Drop-in for MultiScaleDeformableAttention.ms_deform_attn_forward (ops/src/ms_deform_attn.h:20-39):
+ * value [B,S,M,D] f32, spatial_shapes [L,2] i64 (device), level_start_index [L] i64 (device),
+ * sampling_loc [B,Lq,M,L,P,2] f32 normalised (x,y), attn_weight [B,Lq,M,L,P] f32 -> out [B,Lq,M*D] f32. */
+UC_API int uc_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                               const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int L,
+                               int Lq, int P, float* out, void* stream);
+/* Fused form used by the B200 path (B=1, head dim 32): value bf16 [S, M*32]; offlog f32 [Lq, ld] = raw
+ * sampling_offsets (M*L*P*2) followed by attention logits (M*L*P); queries = concatenated level grids;
+ * level_hw host int[2L] (h,w).  out bf16 [Lq, M*32]. */
+UC_API int uc_msda_fused_bf16(const void* value, const float* offlog, int ld_offlog, void* out, const int* level_hw,
+                              int L, int M, int P, void* stream);
+
+/* Fused correlation + softmax over reference positions + label propagation
+ * (external/lib/test/tracker/unicorn_sot.py:95-100; unicorn_vos.py:171-181):
+ *   out[o,j] = sum_i values[o,i] * softmax_i(<embed_ref[i,:], embed_cur[j,:]>)
+ * embed_* [n, C=128] 16-bit rows (NHWC embedding maps), values f32 [n_obj, ldv], out f32 [n_obj, ldo]; n_obj <= 8. */
+UC_API int uc_corr_propagate(const void* embed_ref, int ld_ref, int n_ref, const void* embed_cur, int ld_cur, int n_cur,
+                             int C, int dtype, const float* values, int ldv, int n_obj, float* out, int ldo, void* stream);
+
+/* Head decode (unicorn_head.py:332-334,467-482): per level regobj f32 [HW, ld_ro] = reg(4), obj logit;
+ * cls f32 [HW, ld_cls] = class logits.  regobj/cls/hw/strides are HOST arrays of 3 device pointers / ints.
+ * out f32 [sum HW, 5+ncls] = cx,cy,w,h,sigmoid(obj),sigmoid(cls..). */
+UC_API int uc_head_decode(const float* const* regobj, const float* const* cls, const int* hw, const int* strides,
+                          int ld_ro, int ld_cls, int ncls, float* out, void* stream);
+
+/* postprocess (utils/boxes.py:33-77) on the device: out_dets f32 [<=A, 7] rows (x1,y1,x2,y2,obj,cls_conf,cls_id)
+ * in descending score order, *out_count (device int) = number of rows. */
+UC_API long uc_postprocess_workspace_bytes(int max_anchors);
+UC_API int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, void* workspace,
+                          long workspace_bytes, float* out_dets, int* out_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

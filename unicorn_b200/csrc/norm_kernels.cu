@@ -1,0 +1,348 @@
+// HBM/L2-bound CUDA-core kernels of the backbone: stem conv4x4s4+LN, depthwise 7x7 + LayerNorm, LayerNorm,
+// GroupNorm apply (+SiLU / prior fusion).  All activations NHWC; statistics and arithmetic in fp32.
+#include "uc_common.h"
+#include "../../include/unicorn_b200.h"
+
+namespace uc {
+
+// ------------------------------------------------------------------------------------------------ stem
+// convnext.py:77-80: Conv2d(3, C0, k=4, s=4) + LayerNorm(channels_first, eps 1e-6).
+// img fp32 NCHW [B,3,H,W]; w packed [48][C0] fp32 (k = (ci*4+kh)*4+kw); out NHWC bf16 [B,H/4,W/4,C0].
+// One warp handles 4 horizontally adjacent output pixels; lane owns channels lane+32*i.
+template <int CPL>  // channels per lane = C0/32
+__global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* __restrict__ lnw,
+                                                       const float* __restrict__ lnb, uint16_t* __restrict__ out, int B,
+                                                       int H, int W, float eps) {
+  extern __shared__ float sw[];  // [48][C0]
+  const int C0 = CPL * 32;
+  for (int i = threadIdx.x; i < 48 * C0; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int Ho = H / 4, Wo = W / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups_w = (Wo + 3) / 4;
+  const long total = static_cast<long>(B) * Ho * groups_w;
+  for (long g = static_cast<long>(blockIdx.x) * 8 + warp; g < total; g += static_cast<long>(gridDim.x) * 8) {
+    const int gw = static_cast<int>(g % groups_w);
+    const int oh = static_cast<int>((g / groups_w) % Ho);
+    const int b = static_cast<int>(g / (static_cast<long>(groups_w) * Ho));
+    const int ow0 = gw * 4;
+    // lanes 0..47 each fetch one (ci,kh) row segment of 16 contiguous floats? simpler: each lane loads inputs
+    // k = lane and k = lane+32 (k<48) for the 4 pixels -> shuffle-broadcast in the FMA loop.
+    float in0[4], in1[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int ow = ow0 + p;
+      {
+        const int k = lane, ci = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+        in0[p] = (ow < Wo) ? __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw) : 0.f;
+      }
+      {
+        const int k = lane + 32;
+        if (k < 48) {
+          const int ci = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+          in1[p] = (ow < Wo) ? __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw) : 0.f;
+        } else {
+          in1[p] = 0.f;
+        }
+      }
+    }
+    float acc[4][CPL];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) acc[p][i] = __ldg(bias + lane + 32 * i);
+#pragma unroll 8
+    for (int k = 0; k < 48; ++k) {
+      float xv[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) xv[p] = __shfl_sync(0xffffffffu, k < 32 ? in0[p] : in1[p], k & 31);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const float wv = sw[k * C0 + lane + 32 * i];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][i] = fmaf(xv[p], wv, acc[p][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) s += acc[p][i];
+      const float mean = warp_sum(s) / C0;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { const float d = acc[p][i] - mean; v += d * d; }
+      const float rstd = rsqrtf(warp_sum(v) / C0 + eps);
+      const int ow = ow0 + p;
+      if (ow < Wo) {
+        uint16_t* o = out + ((static_cast<long>(b) * Ho + oh) * Wo + ow) * C0;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int c = lane + 32 * i;
+          o[c] = static_cast<uint16_t>(float_to_bits16((acc[p][i] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c), UC_DT_BF16));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dwconv7 + LN
+// convnext.py:43-45: depthwise 7x7 (pad 3, bias) -> LayerNorm over C (eps 1e-6).  x NHWC bf16 -> y NHWC bf16.
+// w packed [49][C] fp32.  Block = one row segment of PX pixels x all C channels; thread = one channel pair.
+constexpr int kDwPx = 8;
+__global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restrict__ x, const float2* __restrict__ w,
+                                                          const float2* __restrict__ bias, const float2* __restrict__ lnw,
+                                                          const float2* __restrict__ lnb, uint32_t* __restrict__ y, int B,
+                                                          int H, int W, int C2 /* C/2 */, float eps) {
+  __shared__ float red[2][kDwPx][32];
+  const int segs = (W + kDwPx - 1) / kDwPx;
+  const int seg = blockIdx.x % segs;
+  const int oh = (blockIdx.x / segs) % H;
+  const int b = blockIdx.x / (segs * H);
+  const int ow0 = seg * kDwPx;
+  const int cp = threadIdx.x;  // channel pair
+  const bool active = cp < C2;
+  float a0[kDwPx], a1[kDwPx];
+  if (active) {
+    const float2 bb = __ldg(bias + cp);
+#pragma unroll
+    for (int p = 0; p < kDwPx; ++p) { a0[p] = bb.x; a1[p] = bb.y; }
+#pragma unroll 1
+    for (int kh = 0; kh < 7; ++kh) {
+      const int ih = oh + kh - 3;
+      if (ih < 0 || ih >= H) continue;
+      const uint32_t* row = x + (static_cast<long>(b) * H + ih) * W * C2 + cp;
+      float v0[kDwPx + 6], v1[kDwPx + 6];
+#pragma unroll
+      for (int j = 0; j < kDwPx + 6; ++j) {
+        const int iw = ow0 + j - 3;
+        uint32_t u = 0;
+        if (iw >= 0 && iw < W) u = __ldg(row + static_cast<long>(iw) * C2);
+        v0[j] = bf16lo(u); v1[j] = bf16hi(u);
+      }
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        const float2 wv = __ldg(w + (kh * 7 + kw) * C2 + cp);
+#pragma unroll
+        for (int p = 0; p < kDwPx; ++p) {
+          a0[p] = fmaf(v0[p + kw], wv.x, a0[p]);
+          a1[p] = fmaf(v1[p + kw], wv.y, a1[p]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < kDwPx; ++p) { a0[p] = 0.f; a1[p] = 0.f; }
+  }
+  // LayerNorm over channels: two-pass block reduction per pixel
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  float mean[kDwPx], rstd[kDwPx];
+#pragma unroll
+  for (int p = 0; p < kDwPx; ++p) {
+    const float s = warp_sum(a0[p] + a1[p]);
+    if (lane == 0) red[0][p][warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < kDwPx; ++p) {
+    float s = 0.f;
+    for (int i = 0; i < nwarps; ++i) s += red[0][p][i];
+    mean[p] = s / (2 * C2);
+  }
+#pragma unroll
+  for (int p = 0; p < kDwPx; ++p) {
+    const float d0 = a0[p] - mean[p], d1 = a1[p] - mean[p];
+    const float s = warp_sum(active ? d0 * d0 + d1 * d1 : 0.f);
+    if (lane == 0) red[1][p][warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < kDwPx; ++p) {
+    float s = 0.f;
+    for (int i = 0; i < nwarps; ++i) s += red[1][p][i];
+    rstd[p] = rsqrtf(s / (2 * C2) + eps);
+  }
+  if (active) {
+    const float2 gw = __ldg(lnw + cp), gb = __ldg(lnb + cp);
+#pragma unroll
+    for (int p = 0; p < kDwPx; ++p) {
+      const int ow = ow0 + p;
+      if (ow < W) {
+        y[((static_cast<long>(b) * H + oh) * W + ow) * C2 + cp] =
+            pack_bf16((a0[p] - mean[p]) * rstd[p] * gw.x + gb.x, (a1[p] - mean[p]) * rstd[p] * gw.y + gb.y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm rows
+// y[m, :] = LN(x[m, :] (+ r[m, :])) * w + b, one warp per row, C <= 2048, C even.  x/r/y 16-bit rows with strides.
+__global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restrict__ x, int ldx,
+                                                         const uint16_t* __restrict__ r, int ldr,
+                                                         const float* __restrict__ w, const float* __restrict__ bvec,
+                                                         uint16_t* __restrict__ y, int ldy, long M, int C, float eps,
+                                                         int dtype) {
+  const int lane = threadIdx.x & 31;
+  const long m = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  constexpr int MAXI = 32;  // pairs per lane -> C <= 2048
+  float v0[MAXI], v1[MAXI];
+  const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + m * ldx);
+  const uint32_t* rr = r ? reinterpret_cast<const uint32_t*>(r + m * ldr) : nullptr;
+  const int C2 = C >> 1;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = lane + 32 * i;
+    v0[i] = 0.f; v1[i] = 0.f;
+    if (c < C2) {
+      const uint32_t u = __ldg(xr + c);
+      v0[i] = bits16_to_float(u & 0xffffu, dtype); v1[i] = bits16_to_float(u >> 16, dtype);
+      if (rr) {
+        const uint32_t u2 = __ldg(rr + c);
+        v0[i] += bits16_to_float(u2 & 0xffffu, dtype); v1[i] += bits16_to_float(u2 >> 16, dtype);
+      }
+      s += v0[i] + v1[i];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    if (lane + 32 * i < C2) { const float d0 = v0[i] - mean, d1 = v1[i] - mean; q += d0 * d0 + d1 * d1; }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  uint32_t* yr = reinterpret_cast<uint32_t*>(y + m * ldy);
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C2) {
+      const float2 ww = __ldg(reinterpret_cast<const float2*>(w) + c), bb = __ldg(reinterpret_cast<const float2*>(bvec) + c);
+      yr[c] = pack2_16((v0[i] - mean) * rstd * ww.x + bb.x, (v1[i] - mean) * rstd * ww.y + bb.y, dtype);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm apply
+// y = act((x - mean_g) * rstd_g * w[c] + b[c]) (+ prior[pix] * beta[c]) (+ y2 written as y + add2).
+// stats [B][G][2] = {sum, sumsq} over (HW x C/G) accumulated by uc_conv2d.  x/y bf16 NHWC (strided); 8 channels / thread.
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __restrict__ x, int ldx,
+                                                               const float* __restrict__ stats, const float* __restrict__ w,
+                                                               const float* __restrict__ bvec, uint16_t* __restrict__ y, int ldy,
+                                                               int B, long HW, int C, int G, float eps, int act,
+                                                               const float* __restrict__ prior, const float* __restrict__ beta,
+                                                               const uint16_t* __restrict__ add2, int ldadd2,
+                                                               uint16_t* __restrict__ y2, int ldy2) {
+  const int C8 = C >> 3;
+  const long total = static_cast<long>(B) * HW * C8;
+  const int gs = C / G;
+  const float inv_n = 1.f / (static_cast<float>(HW) * gs);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % C8) * 8;
+    const long pix = i / C8;
+    const int b = static_cast<int>(pix / HW);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * ldx + c0);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { f[2 * t] = bf16lo(uw[t]); f[2 * t + 1] = bf16hi(uw[t]); }
+    const float pr = prior ? __ldg(prior + pix) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const int g = c / gs;
+      const float sum = __ldg(stats + (static_cast<long>(b) * G + g) * 2), sq = __ldg(stats + (static_cast<long>(b) * G + g) * 2 + 1);
+      const float mean = sum * inv_n;
+      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      float v = (f[j] - mean) * rsqrtf(var + eps) * __ldg(w + c) + __ldg(bvec + c);
+      if (act == UC_ACT_SILU) v = v / (1.f + __expf(-v));
+      else if (act == UC_ACT_RELU) v = fmaxf(v, 0.f);
+      if (prior) v += pr * __ldg(beta + c);
+      f[j] = v;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(y + pix * ldy + c0) = o;
+    if (y2) {
+      const uint4 a = *reinterpret_cast<const uint4*>(add2 + pix * ldadd2 + c0);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      uint4 o2;
+      o2.x = pack_bf16(f[0] + bf16lo(aw[0]), f[1] + bf16hi(aw[0]));
+      o2.y = pack_bf16(f[2] + bf16lo(aw[1]), f[3] + bf16hi(aw[1]));
+      o2.z = pack_bf16(f[4] + bf16lo(aw[2]), f[5] + bf16hi(aw[2]));
+      o2.w = pack_bf16(f[6] + bf16lo(aw[3]), f[7] + bf16hi(aw[3]));
+      *reinterpret_cast<uint4*>(y2 + pix * ldy2 + c0) = o2;
+    }
+  }
+}
+
+}  // namespace uc
+
+using namespace uc;
+
+extern "C" int uc_stem_ln(const float* img, const float* w48, const float* bias, const float* lnw, const float* lnb,
+                          void* out_bf16, int B, int H, int W, int C0, float eps, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!img || !w48 || !bias || !lnw || !lnb || !out_bf16) return set_error(UC_EINVAL, "uc_stem_ln: null pointer");
+  if (H % 4 || W % 4 || C0 % 32 || C0 > 256) return set_error(UC_EINVAL, "uc_stem_ln: need H%%4==0, W%%4==0, C0%%32==0, C0<=256");
+  const long groups = static_cast<long>(B) * (H / 4) * ((W / 4 + 3) / 4);
+  const int grid = static_cast<int>(std::min<long>((groups + 7) / 8, static_cast<long>(num_sms()) * 8));
+  const size_t smem = static_cast<size_t>(48) * C0 * sizeof(float);
+  uint16_t* out = static_cast<uint16_t*>(out_bf16);
+#define UC_STEM(CPL)                                                                                                   \
+  case CPL: {                                                                                                          \
+    cudaFuncSetAttribute(stem_ln_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);                 \
+    stem_ln_kernel<CPL><<<grid, 256, smem, stream>>>(img, w48, bias, lnw, lnb, out, B, H, W, eps);                     \
+  } break;
+  switch (C0 / 32) {
+    UC_STEM(1) UC_STEM(2) UC_STEM(3) UC_STEM(4) UC_STEM(6) UC_STEM(8)
+    default: return set_error(UC_EINVAL, "uc_stem_ln: unsupported C0 %d", C0);
+  }
+#undef UC_STEM
+  return check_launch("uc_stem_ln");
+}
+
+extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias, const float* lnw, const float* lnb,
+                             void* y_bf16, int B, int H, int W, int C, float eps, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x_bf16 || !w49 || !bias || !lnw || !lnb || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7_ln: null pointer");
+  if (C % 2 || C > 1536 || C < 2) return set_error(UC_EINVAL, "uc_dwconv7_ln: C must be even and <= 1536");
+  const int C2 = C / 2;
+  const int threads = (C2 + 31) / 32 * 32;
+  const long blocks = static_cast<long>(B) * H * ((W + kDwPx - 1) / kDwPx);
+  if (blocks > 0x7fffffffL) return set_error(UC_EINVAL, "uc_dwconv7_ln: too many blocks");
+  dwconv7_ln_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      static_cast<const uint32_t*>(x_bf16), reinterpret_cast<const float2*>(w49), reinterpret_cast<const float2*>(bias),
+      reinterpret_cast<const float2*>(lnw), reinterpret_cast<const float2*>(lnb), static_cast<uint32_t*>(y_bf16), B, H, W, C2, eps);
+  return check_launch("uc_dwconv7_ln");
+}
+
+extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, const float* w, const float* b, void* y,
+                            int ldy, long M, int C, float eps, int dtype, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !w || !b || !y) return set_error(UC_EINVAL, "uc_layernorm: null pointer");
+  if (C % 2 || C > 2048 || ldx % 2 || ldy % 2 || (res && ldres % 2)) return set_error(UC_EINVAL, "uc_layernorm: C even <= 2048, even strides");
+  if (dtype != UC_BF16 && dtype != UC_F16) return set_error(UC_EINVAL, "uc_layernorm: 16-bit dtypes only");
+  const long blocks = (M + 7) / 8;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx,
+                                                                      static_cast<const uint16_t*>(res), ldres, w, b,
+                                                                      static_cast<uint16_t*>(y), ldy, M, C, eps, dtype);
+  return check_launch("uc_layernorm");
+}
+
+extern "C" int uc_groupnorm_apply(const void* x, int ldx, const float* stats, const float* w, const float* b, void* y,
+                                  int ldy, int B, long HW, int C, int G, float eps, int act, const float* prior,
+                                  const float* beta, const void* add2, int ldadd2, void* y2, int ldy2, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !stats || !w || !b || !y) return set_error(UC_EINVAL, "uc_groupnorm_apply: null pointer");
+  if (C % 8 || ldx % 8 || ldy % 8 || C % G) return set_error(UC_EINVAL, "uc_groupnorm_apply: C, ldx, ldy multiples of 8; C %% G == 0");
+  if ((prior != nullptr) != (beta != nullptr)) return set_error(UC_EINVAL, "uc_groupnorm_apply: prior and beta go together");
+  if (y2 && (!add2 || ldadd2 % 8 || ldy2 % 8)) return set_error(UC_EINVAL, "uc_groupnorm_apply: bad second output");
+  const long total = static_cast<long>(B) * HW * (C / 8);
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16));
+  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx, stats, w, b,
+                                                   static_cast<uint16_t*>(y), ldy, B, HW, C, G, eps, act, prior, beta,
+                                                   static_cast<const uint16_t*>(add2), ldadd2, static_cast<uint16_t*>(y2), ldy2);
+  return check_launch("uc_groupnorm_apply");
+}

@@ -86,3 +86,185 @@ def linear(x2d, w_packed, **kw):
         res = res.as_strided((1, 1, M, res.shape[1]), (M * res.stride(0), M * res.stride(0), res.stride(0), 1))
     y = conv2d(x4, w_packed, 1, 1, out=out, res=res, **kw)
     return y.as_strided((M, y.shape[3]), (y.stride(2), 1))
+
+
+# ------------------------------------------------------------------------------------------- other entry points
+def _L():
+    return _lib.lib()
+
+
+def _S():
+    return _lib.stream_ptr()
+
+
+_f = ctypes.c_float
+_i = ctypes.c_int
+_l = ctypes.c_long
+
+
+def pack_stem_weight(w):
+    """[C0,3,4,4] -> [48, C0] fp32 (k = (ci*4+kh)*4+kw)."""
+    return w.reshape(w.shape[0], 48).t().contiguous().float()
+
+
+def pack_dw_weight(w):
+    """[C,1,7,7] -> [49, C] fp32."""
+    return w.reshape(w.shape[0], 49).t().contiguous().float()
+
+
+def stem_ln(img, w48, bias, lnw, lnb, eps=1e-6):
+    B, _, H, W = img.shape
+    C0 = w48.shape[1]
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    out = torch.empty(B, H // 4, W // 4, C0, dtype=torch.bfloat16, device=img.device)
+    _lib.check(_L().uc_stem_ln(_p(img), _p(w48), _p(bias), _p(lnw), _p(lnb), _p(out), B, H, W, C0, _f(eps), _S()), "uc_stem_ln")
+    return out
+
+
+def dwconv7_ln(x, w49, bias, lnw, lnb, eps=1e-6, out=None):
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_L().uc_dwconv7_ln(_p(x), _p(w49), _p(bias), _p(lnw), _p(lnb), _p(out), B, H, W, C, _f(eps), _S()), "uc_dwconv7_ln")
+    return out
+
+
+def layernorm(x2d, w, b, eps, res=None, out=None):
+    """rows [M, C] (unit inner stride)."""
+    M, C = x2d.shape
+    if out is None:
+        out = torch.empty(M, C, dtype=x2d.dtype, device=x2d.device)
+    _lib.check(_L().uc_layernorm(_p(x2d), x2d.stride(0), _p(res), res.stride(0) if res is not None else 0, _p(w), _p(b),
+                                 _p(out), out.stride(0), _l(M), C, _f(eps), _DT[x2d.dtype], _S()), "uc_layernorm")
+    return out
+
+
+def groupnorm_apply(x, stats, w, b, G, eps, act, out=None, prior=None, beta=None, add2=None, out2=None):
+    """x NHWC view; in-place when out is None."""
+    B, H, W, C = x.shape
+    if out is None:
+        out = x
+    ld2 = _nhwc_ld(add2) if add2 is not None else 0
+    _lib.check(_L().uc_groupnorm_apply(_p(x), _nhwc_ld(x), _p(stats), _p(w), _p(b), _p(out), _nhwc_ld(out), B, _l(H * W), C, G,
+                                       _f(eps), act, _p(prior), _p(beta), _p(add2), ld2, _p(out2),
+                                       _nhwc_ld(out2) if out2 is not None else 0, _S()), "uc_groupnorm_apply")
+    return out
+
+
+def copy_upsample(src, dst, up):
+    B, Hs, Ws, C = src.shape
+    assert dst.shape == (B, Hs * up, Ws * up, C)
+    _lib.check(_L().uc_copy_upsample(_p(src), _nhwc_ld(src), _p(dst), _nhwc_ld(dst), B, Hs, Ws, C, up, _S()), "uc_copy_upsample")
+    return dst
+
+
+def pixel_shuffle2(x, out=None):
+    B, H, W, C4 = x.shape
+    Co = C4 // 4
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Co, dtype=x.dtype, device=x.device)
+    _lib.check(_L().uc_pixel_shuffle2(_p(x), _nhwc_ld(x), _p(out), _nhwc_ld(out), B, H, W, Co, _S()), "uc_pixel_shuffle2")
+    return out
+
+
+def bilinear(src, Hd, Wd, scale_h=0.0, scale_w=0.0, out=None):
+    """src fp32 [..., Hs, Ws] contiguous planes."""
+    Hs, Ws = src.shape[-2:]
+    P = src.numel() // (Hs * Ws)
+    if out is None:
+        out = torch.empty(*src.shape[:-2], Hd, Wd, dtype=torch.float32, device=src.device)
+    _lib.check(_L().uc_bilinear_f32(_p(src), _p(out), P, Hs, Ws, Hd, Wd, _f(scale_h), _f(scale_w), _S()), "uc_bilinear_f32")
+    return out
+
+
+def add(a2d, b2d, out=None):
+    M, C = a2d.shape
+    if out is None:
+        out = torch.empty(M, C, dtype=a2d.dtype, device=a2d.device)
+    _lib.check(_L().uc_add(_p(a2d), a2d.stride(0), _p(b2d), b2d.stride(0), _p(out), out.stride(0), _l(M), C, _DT[a2d.dtype], _S()), "uc_add")
+    return out
+
+
+def nchw_to_nhwc(x, dtype=torch.bfloat16, out=None):
+    B, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, H, W, C, dtype=dtype, device=x.device)
+    _lib.check(_L().uc_nchw_f32_to_nhwc(_p(x), _p(out), _nhwc_ld(out), B, C, _l(H * W), _DT[out.dtype], _S()), "uc_nchw_f32_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x):
+    B, H, W, C = x.shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    _lib.check(_L().uc_nhwc_to_nchw_f32(_p(x), _nhwc_ld(x), _p(out), B, C, _l(H * W), _DT[x.dtype], _S()), "uc_nhwc_to_nchw_f32")
+    return out
+
+
+def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """Reference operator semantics (fp32)."""
+    B, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    out = torch.empty(B, Lq, M * D, dtype=torch.float32, device=value.device)
+    _lib.check(_L().uc_msda_forward_f32(_p(value), _p(spatial_shapes), _p(level_start_index), _p(sampling_loc), _p(attn_weight),
+                                        B, S, M, D, L, Lq, P, _p(out), _S()), "uc_msda_forward_f32")
+    return out
+
+
+def msda_fused(value, offlog, level_hw, M=8, P=4, out=None):
+    L = len(level_hw)
+    Lq = sum(h * w for h, w in level_hw)
+    assert value.shape == (Lq, M * 32) and value.dtype == torch.bfloat16 and value.is_contiguous()
+    assert offlog.dtype == torch.float32 and offlog.shape[0] == Lq and offlog.shape[1] >= M * L * P * 3
+    if out is None:
+        out = torch.empty(Lq, M * 32, dtype=torch.bfloat16, device=value.device)
+    hw = (ctypes.c_int * (2 * L))(*[v for pair in level_hw for v in pair])
+    _lib.check(_L().uc_msda_fused_bf16(_p(value), _p(offlog), offlog.stride(0), _p(out), hw, L, M, P, _S()), "uc_msda_fused_bf16")
+    return out
+
+
+def corr_propagate(embed_ref, embed_cur, values, out=None):
+    """embed_* [n, 128] 16-bit rows; values fp32 [n_obj, n_ref] -> fp32 [n_obj, n_cur]."""
+    n_ref, C = embed_ref.shape
+    n_cur = embed_cur.shape[0]
+    n_obj = values.shape[0]
+    assert values.dtype == torch.float32 and values.stride(1) == 1 and values.shape[1] == n_ref
+    if out is None:
+        out = torch.empty(n_obj, n_cur, dtype=torch.float32, device=values.device)
+    _lib.check(_L().uc_corr_propagate(_p(embed_ref), embed_ref.stride(0), n_ref, _p(embed_cur), embed_cur.stride(0), n_cur, C,
+                                      _DT[embed_ref.dtype], _p(values), values.stride(0), n_obj, _p(out), out.stride(0), _S()),
+               "uc_corr_propagate")
+    return out
+
+
+def head_decode(regobj, cls, hw, strides, ncls, out=None):
+    A = sum(h * w for h, w in hw)
+    if out is None:
+        out = torch.empty(1, A, 5 + ncls, dtype=torch.float32, device=regobj[0].device)
+    ro = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in regobj])
+    cl = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in cls])
+    hwa = (ctypes.c_int * 6)(*[v for pair in hw for v in pair])
+    st = (ctypes.c_int * 3)(*strides)
+    _lib.check(_L().uc_head_decode(ro, cl, hwa, st, regobj[0].shape[-1], cls[0].shape[-1], ncls, _p(out), _S()), "uc_head_decode")
+    return out
+
+
+class PostWorkspace:
+    def __init__(self, max_anchors, device):
+        fn = _L().uc_postprocess_workspace_bytes
+        fn.restype = ctypes.c_long
+        self.nbytes = fn(max_anchors)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.dets = torch.empty(max_anchors, 7, dtype=torch.float32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.max_anchors = max_anchors
+
+
+def postprocess_device(pred, ncls, conf, nms, ws):
+    """pred fp32 [A, 5+ncls] (decoded).  Launches only; ws.dets / ws.count hold the result."""
+    A = pred.shape[0]
+    assert pred.is_contiguous() and pred.dtype == torch.float32 and A <= ws.max_anchors
+    _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
+               "uc_postprocess")
+    return ws.dets, ws.count

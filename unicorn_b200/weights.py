@@ -153,7 +153,7 @@ def make_state_dict(cfg_name, seed=0):
             t = n(*shape) * (0.5 / 16.0)
         elif name.endswith(".bias"):
             if any(k in name for k in ("obj_preds", "cls_preds")):
-                t = -3.0 + 1.5 * n(*shape)
+                t = -4.0 + 1.5 * n(*shape)
             elif "reg_preds" in name:  # wider boxes so that NMS has real work
                 t = 0.1 * n(*shape) + torch.tensor([0.0, 0.0, 1.2, 1.2])
             elif any(k in name for k in (".bn.", "norm", "refine", "tower")) and len(shape) == 1 and ".0.weight" not in name:
