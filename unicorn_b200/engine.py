@@ -1,0 +1,316 @@
+"""UnicornEngine — the per-frame inference hot path as a static sequence of sm_100a kernel launches.
+
+Host-side mirror of the reference model (unicorn/models/unicorn.py `Unicorn`, backbone/yolo_pafpn_new.py,
+backbone/convnext.py, deformable_transformer.py, unicorn_head.py) with a B200-first data layout:
+
+  * activations live in HBM as NHWC bf16 (channels contiguous): LayerNorm/Linear of ConvNeXt need no permutes and
+    every convolution is an implicit GEMM whose A operand is fetched by TMA boxes straight from the NHWC map;
+  * concatenations (PAFPN, CSP) are never materialised by copies: producers write into channel slices of one buffer;
+  * GroupNorm statistics are accumulated in the producing convolution's epilogue, the normalise+SiLU pass runs in place;
+  * the embedding used for correlation is written as fp16 (the reference casts to .half() before torch.mm);
+  * prediction logits, statistics, priors and boxes stay fp32.
+
+All buffers are allocated on first use per input resolution and then reused, so a steady-state frame performs no
+allocation and can be captured in a CUDA graph (see unicorn_b200/sot.py).  torch is used only as the device-memory
+allocator and stream/graph plumbing; every arithmetic step is a launch through the C ABI (unicorn_b200/ops.py).
+"""
+import torch
+
+from . import ops
+from .weights import CONFIGS
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GELU, ops.ACT_SILU
+BF16, F16, F32 = torch.bfloat16, torch.float16, torch.float32
+STRIDES = (8, 16, 32)
+
+
+class _ConvGN:
+    """BaseConv: conv (no bias) -> GroupNorm -> SiLU (network_blocks.py:29-51, GN via exp/unicorn_track.py:450-470)."""
+
+    def __init__(self, w, gw, gb, k, stride, groups=16, eps=1e-3, bias=None):
+        self.w, self.gw, self.gb, self.k, self.stride, self.groups, self.eps, self.bias = w, gw, gb, k, stride, groups, eps, bias
+        self.cout = w.shape[0]
+
+
+class UnicornEngine:
+    def __init__(self, state_dict, cfg_name, device="cuda"):
+        ops._lib.check(ops._lib.lib().uc_check_device(), "uc_check_device")  # fail loudly without an sm_100 GPU
+        self.cfg_name = cfg_name
+        self.cfg = CONFIGS[cfg_name]
+        self.dev = torch.device(device)
+        self.dims = self.cfg["dims"]
+        self.depths = self.cfg["depths"]
+        self.ncls = self.cfg["num_classes"]
+        self._bufs = {}
+        self._stats_arena = None
+        self._stats_used = 0
+        self._pos_cache = {}
+        self._load(state_dict)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _load(self, sd):
+        dev = self.dev
+        f = lambda k: sd[k].to(dev, F32).contiguous()  # noqa: E731
+        pw = lambda k: ops.pack_conv_weight(sd[k].to(dev, F32))  # noqa: E731
+        P = {}
+        b = "backbone.backbone."
+        P["stem"] = (ops.pack_stem_weight(sd[b + "downsample_layers.0.0.weight"].to(dev)), f(b + "downsample_layers.0.0.bias"),
+                     f(b + "downsample_layers.0.1.weight"), f(b + "downsample_layers.0.1.bias"))
+        for i in range(1, 4):
+            P[f"down{i}"] = (f(b + f"downsample_layers.{i}.0.weight"), f(b + f"downsample_layers.{i}.0.bias"),
+                             pw(b + f"downsample_layers.{i}.1.weight"), f(b + f"downsample_layers.{i}.1.bias"))
+            P[f"norm{i}"] = (f(b + f"norm{i}.weight"), f(b + f"norm{i}.bias"))
+
+        def block(p):
+            return dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
+                        lnb=f(p + "norm.bias"), w1=pw(p + "pwconv1.weight"), b1=f(p + "pwconv1.bias"), w2=pw(p + "pwconv2.weight"),
+                        b2=f(p + "pwconv2.bias"), gamma=f(p + "gamma"))
+
+        P["stages"] = [[block(b + f"stages.{i}.{j}.") for j in range(self.depths[i])] for i in range(4)]
+
+        def cgn(p, k, stride=1):
+            return _ConvGN(pw(p + "conv.weight"), f(p + "bn.weight"), f(p + "bn.bias"), k, stride)
+
+        def csp(p):
+            c1, c2 = cgn(p + "conv1.", 1), cgn(p + "conv2.", 1)
+            fused = _ConvGN(torch.cat([c1.w, c2.w], 0).contiguous(), torch.cat([c1.gw, c2.gw]).contiguous(),
+                            torch.cat([c1.gb, c2.gb]).contiguous(), 1, 1, groups=32)
+            return dict(c12=fused, c3=cgn(p + "conv3.", 1), m=[(cgn(p + f"m.{i}.conv1.", 1), cgn(p + f"m.{i}.conv2.", 3)) for i in range(3)])
+
+        n = "backbone."
+        P["lateral_conv0"], P["reduce_conv1"] = cgn(n + "lateral_conv0.", 1), cgn(n + "reduce_conv1.", 1)
+        P["bu_conv2"], P["bu_conv1"] = cgn(n + "bu_conv2.", 3, 2), cgn(n + "bu_conv1.", 3, 2)
+        for name in ("C3_p4", "C3_p3", "C3_n3", "C3_n4"):
+            P[name] = csp(n + name + ".")
+        # interaction
+        P["bottleneck"] = _ConvGN(pw("bottleneck.0.weight"), f("bottleneck.1.weight"), f("bottleneck.1.bias"), 1, 1, groups=32, eps=1e-5,
+                                  bias=f("bottleneck.0.bias"))
+        t = "transformer.encoder.layers.0."
+        P["value_proj"] = (pw(t + "self_attn.value_proj.weight"), f(t + "self_attn.value_proj.bias"))
+        P["offlog"] = (ops.pack_conv_weight(torch.cat([sd[t + "self_attn.sampling_offsets.weight"], sd[t + "self_attn.attention_weights.weight"]], 0).to(dev, F32)),
+                       torch.cat([sd[t + "self_attn.sampling_offsets.bias"], sd[t + "self_attn.attention_weights.bias"]]).to(dev, F32).contiguous())
+        P["output_proj"] = (pw(t + "self_attn.output_proj.weight"), f(t + "self_attn.output_proj.bias"))
+        P["norm1"] = (f(t + "norm1.weight"), f(t + "norm1.bias"))
+        P["linear1"] = (pw(t + "linear1.weight"), f(t + "linear1.bias"))
+        P["linear2"] = (pw(t + "linear2.weight"), f(t + "linear2.bias"))
+        P["norm2"] = (f(t + "norm2.weight"), f(t + "norm2.bias"))
+        P["level_embed"] = f("transformer.level_embed")
+        P["pos_tab"] = (f("pos_emb.col_embed.weight"), f("pos_emb.row_embed.weight"))
+        P["up1"] = (pw("upsample_layer.1.weight"), f("upsample_layer.1.bias"))
+        P["up3"] = (pw("upsample_layer.3.weight"), f("upsample_layer.3.bias"))
+        # head
+        h = "head."
+        P["head"] = []
+        for k in range(3):
+            lvl = dict(stem=cgn(h + f"stems.{k}.", 1), beta=f(h + f"beta_{k}").reshape(-1).contiguous(),
+                       att=[block(h + f"att_layers.{k}.{i}.") for i in range(3)],
+                       cls=[cgn(h + f"cls_convs.{k}.{i}.", 3) for i in range(4)], reg=[cgn(h + f"reg_convs.{k}.{i}.", 3) for i in range(4)])
+            for sfx in ("", "_sot"):
+                ro_w = torch.cat([sd[h + f"reg_preds{sfx}.{k}.weight"], sd[h + f"obj_preds{sfx}.{k}.weight"]], 0).to(dev, F32)
+                ro_b = torch.zeros(8, device=dev)
+                ro_b[:5] = torch.cat([sd[h + f"reg_preds{sfx}.{k}.bias"], sd[h + f"obj_preds{sfx}.{k}.bias"]]).to(dev)
+                cw = sd[h + f"cls_preds{sfx}.{k}.weight"].to(dev, F32)
+                cb = torch.zeros(8, device=dev)
+                cb[:cw.shape[0]] = sd[h + f"cls_preds{sfx}.{k}.bias"].to(dev)
+                lvl["pred" + sfx] = (ops.pack_conv_weight(ro_w), ro_b, ops.pack_conv_weight(cw), cb, cw.shape[0])
+            P["head"].append(lvl)
+        self.P = P
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype=BF16, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    def begin_frame(self):
+        """Zero the GroupNorm statistics arena (one memset per frame; slots are handed out in call order)."""
+        if self._stats_arena is None:
+            self._stats_arena = torch.zeros(512, 32, 2, dtype=F32, device=self.dev)
+        else:
+            self._stats_arena.zero_()
+        self._stats_used = 0
+
+    def _stats(self, groups):
+        s = self._stats_arena[self._stats_used]
+        self._stats_used += 1
+        assert self._stats_used <= self._stats_arena.shape[0]
+        return s[:groups]
+
+    # ------------------------------------------------------------------------------------------ building blocks
+    def conv_gn(self, x, c, out, act=ACT_SILU, prior=None, beta=None, add2=None, out2=None):
+        """x NHWC view -> out NHWC view (may be a channel slice)."""
+        st = self._stats(c.groups)
+        ops.conv2d(x, c.w, c.k, c.k, c.stride, (c.k - 1) // 2, bias=c.bias, out=out, gn_stats=st, gn_groups=c.groups)
+        ops.groupnorm_apply(out, st, c.gw, c.gb, c.groups, c.eps, act, prior=prior, beta=beta, add2=add2, out2=out2)
+        return out
+
+    def convnext_block(self, x, bp, tag):
+        """In place on x (NHWC contiguous) — convnext.py:41-54."""
+        B, H, W, C = x.shape
+        t = ops.dwconv7_ln(x, bp["dw"], bp["dwb"], bp["lnw"], bp["lnb"], 1e-6, out=self.buf(tag + ".t", x.shape))
+        hid = ops.conv2d(t, bp["w1"], 1, 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
+        ops.conv2d(hid, bp["w2"], 1, 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
+        return x
+
+    def csp(self, x, cp, out, tag):
+        """CSPLayer (network_blocks.py:147-185) on a NHWC (possibly concatenated) buffer x -> out."""
+        B, H, W, _ = x.shape
+        hdim = cp["c12"].cout // 2
+        cat = self.buf(tag + ".cat", (B, H, W, 2 * hdim))
+        self.conv_gn(x, cp["c12"], cat)  # [x_1 | x_2]
+        cur = cat[..., :hdim]
+        for i, (c1, c2) in enumerate(cp["m"]):
+            t = self.conv_gn(cur, c1, self.buf(tag + ".m1", (B, H, W, hdim)))
+            dst = cat[..., :hdim] if i == len(cp["m"]) - 1 else self.buf(tag + f".m2_{i % 2}", (B, H, W, hdim))
+            cur = self.conv_gn(t, c2, dst)
+        return self.conv_gn(cat, cp["c3"], out)
+
+    # ------------------------------------------------------------------------------------------ backbone + neck
+    def backbone(self, img, tag="cur"):
+        """img fp32 NCHW [1,3,H,W] -> (fpn_outs (p3,p4,p5) NHWC bf16, seq_dict{feat NHWC view, h, w}).
+        ConvNeXt.forward_features (convnext.py:141-154) + YOLOPAFPNNEW.forward (yolo_pafpn_new.py:137-155)."""
+        P, d = self.P, self.dims
+        B, _, H, W = img.shape
+        assert B == 1 and H % 32 == 0 and W % 32 == 0
+        h8, w8, h16, w16, h32, w32 = H // 8, W // 8, H // 16, W // 16, H // 32, W // 32
+        # concat buffers of the neck (producers write into slices)
+        cat_p4 = self.buf(tag + ".cat_p4", (1, h16, w16, 2 * d[2]))
+        cat_p3 = self.buf(tag + ".cat_p3", (1, h8, w8, 2 * d[1]))
+        cat_n3 = self.buf(tag + ".cat_n3", (1, h16, w16, 2 * d[1]))
+        cat_n4 = self.buf(tag + ".cat_n4", (1, h32, w32, 2 * d[2]))
+        x = ops.stem_ln(img, *P["stem"])
+        feats = {}
+        for i in range(4):
+            if i > 0:
+                lw, lb, cw, cb = P[f"down{i}"]
+                Bx, Hx, Wx, Cx = x.shape
+                t = ops.layernorm(x.view(-1, Cx), lw, lb, 1e-6, out=self.buf(f"{tag}.dn{i}", (Hx * Wx, Cx))).view(1, Hx, Wx, Cx)
+                x = ops.conv2d(t, cw, 2, 2, 2, 0, bias=cb, out=self.buf(f"{tag}.x{i}", (1, Hx // 2, Wx // 2, d[i])))
+            for j, bp in enumerate(P["stages"][i]):
+                self.convnext_block(x, bp, f"{tag}.s{i}")
+            if i >= 1:
+                nw, nb = P[f"norm{i}"]
+                Bx, Hx, Wx, Cx = x.shape
+                dst = {1: cat_p3[..., d[1]:], 2: cat_p4[..., d[2]:], 3: self.buf(tag + ".x0n", (1, h32, w32, d[3]))}[i]
+                ops.layernorm(x.view(-1, Cx), nw, nb, 1e-6, out=_rows(dst))
+                feats[i] = dst
+        x2n, x1n, x0n = feats[1], feats[2], feats[3]
+        # top-down
+        fpn_out0 = self.conv_gn(x0n, P["lateral_conv0"], cat_n4[..., d[2]:])
+        ops.copy_upsample(fpn_out0, cat_p4[..., :d[2]], 2)
+        f_out0 = self.csp(cat_p4, P["C3_p4"], self.buf(tag + ".f_out0", (1, h16, w16, d[2])), tag + ".C3_p4")
+        fpn_out1 = self.conv_gn(f_out0, P["reduce_conv1"], cat_n3[..., d[1]:])
+        ops.copy_upsample(fpn_out1, cat_p3[..., :d[1]], 2)
+        pan_out2 = self.csp(cat_p3, P["C3_p3"], self.buf(tag + ".pan_out2", (1, h8, w8, d[1])), tag + ".C3_p3")
+        # bottom-up
+        self.conv_gn(pan_out2, P["bu_conv2"], cat_n3[..., :d[1]])
+        pan_out1 = self.csp(cat_n3, P["C3_n3"], self.buf(tag + ".pan_out1", (1, h16, w16, d[2])), tag + ".C3_n3")
+        self.conv_gn(pan_out1, P["bu_conv1"], cat_n4[..., :d[2]])
+        pan_out0 = self.csp(cat_n4, P["C3_n4"], self.buf(tag + ".pan_out0", (1, h32, w32, d[3])), tag + ".C3_n4")
+        return (pan_out2, pan_out1, pan_out0), {"feat": x1n, "h": h16, "w": w16}
+
+    # ------------------------------------------------------------------------------------------ interaction
+    def pos_tokens(self, h, w):
+        """[2, h*w, 256] bf16: learned pos-emb (position_encoding.py:25-36) resized to (h,w) + level embed
+        (deformable_transformer.py:74).  Cached per resolution (identity bicubic of unicorn.py:249 dropped)."""
+        key = (h, w)
+        if key not in self._pos_cache:
+            col, row = self.P["pos_tab"]
+            sz = col.shape[0]
+            tab = torch.cat([col.unsqueeze(0).repeat(sz, 1, 1), row.unsqueeze(1).repeat(1, sz, 1)], dim=-1).permute(2, 0, 1).contiguous()
+            pos = ops.bilinear(tab.unsqueeze(0), h, w)  # [1,256,h,w] fp32
+            toks = pos[0].permute(1, 2, 0).reshape(1, h * w, 256) + self.P["level_embed"].view(2, 1, 256)
+            self._pos_cache[key] = (toks.to(BF16).contiguous(), pos)
+        return self._pos_cache[key]
+
+    def project_tokens(self, feat, lvl, src, q):
+        """bottleneck conv1x1+bias -> GN32 (unicorn.py:36-38,265); writes rows of `src` and `q = src + pos + level_embed`."""
+        h, w = feat.shape[1:3]
+        pos_lvl = self.pos_tokens(h, w)[0]
+        n = h * w
+        dst = src[lvl * n:(lvl + 1) * n].view(1, h, w, 256)
+        self.conv_gn(feat, self.P["bottleneck"], dst, act=ACT_NONE, add2=pos_lvl[lvl].view(1, h, w, 256),
+                     out2=q[lvl * n:(lvl + 1) * n].view(1, h, w, 256))
+
+    def encoder(self, src, q, h, w):
+        """One deformable encoder layer over the two frames as two levels (deformable_transformer.py:122-131,
+        ops/modules/ms_deform_attn.py:94-115).  src, q: [2hw, 256] bf16.  Returns [2hw, 256] bf16 (new buffer)."""
+        P = self.P
+        S = src.shape[0]
+        value = ops.linear(src, P["value_proj"][0], bias=P["value_proj"][1], out=self.buf("enc.value", (S, 256)))
+        offlog = ops.linear(q, P["offlog"][0], bias=P["offlog"][1], out=self.buf("enc.offlog", (S, 192), F32))
+        att = ops.msda_fused(value, offlog, [(h, w), (h, w)], 8, 4, out=self.buf("enc.att", (S, 256)))
+        x = ops.linear(att, P["output_proj"][0], bias=P["output_proj"][1], res=src, out=self.buf("enc.x", (S, 256)))
+        ops.layernorm(x, *P["norm1"], 1e-5, out=x)
+        hid = ops.linear(x, P["linear1"][0], bias=P["linear1"][1], act=ACT_RELU, out=self.buf("enc.hid", (S, 1024)))
+        y = ops.linear(hid, P["linear2"][0], bias=P["linear2"][1], res=x, out=self.buf("enc.y", (S, 256)))
+        ops.layernorm(y, *P["norm2"], 1e-5, out=y)
+        return y
+
+    def interaction(self, feat0, feat1, cache_ref=False):
+        """Unicorn.forward_deform_interact (unicorn.py:260-276): -> (new_feat0, new_feat1) NHWC bf16 [1,h,w,256].
+        cache_ref=True reuses the rows of frame 0 already projected by a previous call (fixed SOT reference)."""
+        h, w = feat1.shape[1:3]
+        n = h * w
+        src, q = self.buf("enc.src", (2 * n, 256)), self.buf("enc.q", (2 * n, 256))
+        if not cache_ref:
+            self.project_tokens(feat0, 0, src, q)
+        self.project_tokens(feat1, 1, src, q)
+        y = self.encoder(src, q, h, w)
+        return y[:n].view(1, h, w, 256), y[n:].view(1, h, w, 256)
+
+    def upsample(self, feat, tag):
+        """Unicorn.forward_upsample (unicorn.py:41-44,311-313): [1,h,w,256] -> embedding [1,2h,2w,128] fp16."""
+        _, h, w, _ = feat.shape
+        ps = ops.pixel_shuffle2(feat, out=self.buf(tag + ".ps", (1, 2 * h, 2 * w, 64)))
+        t = ops.conv2d(ps, self.P["up1"][0], 3, 3, 1, 1, bias=self.P["up1"][1], act=ACT_RELU, out=self.buf(tag + ".u1", (1, 2 * h, 2 * w, 256)))
+        return ops.conv2d(t, self.P["up3"][0], 3, 3, 1, 1, bias=self.P["up3"][1], out=self.buf(tag + ".emb", (1, 2 * h, 2 * w, 128), F16))
+
+    # ------------------------------------------------------------------------------------------ correlation
+    def propagate(self, embed_ref, embed_cur, values):
+        """unicorn_sot.py:88-105: label propagation + prior pyramid.  values fp32 [K, h8*w8] -> 3 fp32 maps [K,h,w]."""
+        _, hh, ww, C = embed_cur.shape
+        K = values.shape[0]
+        coarse = ops.corr_propagate(embed_ref.view(-1, C), embed_cur.view(-1, C), values, out=self.buf("corr.out", (K, hh * ww), F32))
+        c0 = coarse.view(K, hh, ww)
+        c1 = ops.bilinear(c0, hh // 2, ww // 2, 2.0, 2.0, out=self.buf("corr.p1", (K, hh // 2, ww // 2), F32))
+        c2 = ops.bilinear(c0, hh // 4, ww // 4, 4.0, 4.0, out=self.buf("corr.p2", (K, hh // 4, ww // 4), F32))
+        return (c0, c1, c2)
+
+    # ------------------------------------------------------------------------------------------ head
+    def head(self, fpn, priors, mode):
+        """UnicornHead.forward eval branch (unicorn_head.py:267-336) + decode_outputs (:467-482).
+        fpn: 3 NHWC bf16 maps; priors: 3 fp32 [1,h,w] maps or None (MOT: zero prior == no fusion term).
+        Returns fp32 [1, A, 5+ncls_mode]."""
+        sfx = "_sot" if mode == "sot" else ""
+        ro_outs, cls_outs, hw = [], [], []
+        ncls = 1 if mode == "sot" else self.ncls
+        for k in range(3):
+            L = self.P["head"][k]
+            _, h, w, _ = fpn[k].shape
+            x = self.buf(f"head{k}.x", (1, h, w, 256))
+            pr = priors[k].reshape(-1) if priors is not None else None
+            self.conv_gn(fpn[k], L["stem"], x, prior=pr, beta=L["beta"] if pr is not None else None)
+            for i in range(3):
+                self.convnext_block(x, L["att"][i], f"head{k}.att")
+            feats = []
+            for name in ("cls", "reg"):
+                cur = x
+                for i, c in enumerate(L[name]):
+                    cur = self.conv_gn(cur, c, self.buf(f"head{k}.{name}{i % 2}", (1, h, w, 256)))
+                feats.append(cur)
+            row, rob, cw, cb, _ = L["pred" + sfx]
+            cls_outs.append(ops.conv2d(feats[0], cw, 1, 1, bias=cb, out=self.buf(f"head{k}.clso", (1, h, w, 8), F32)))
+            ro_outs.append(ops.conv2d(feats[1], row, 1, 1, bias=rob, out=self.buf(f"head{k}.roo", (1, h, w, 8), F32)))
+            hw.append((h, w))
+        A = sum(h * w for h, w in hw)
+        return ops.head_decode(ro_outs, cls_outs, hw, STRIDES, ncls, out=self.buf(f"head.out{ncls}", (1, A, 5 + ncls), F32))
+
+
+def _rows(t):
+    """[1,H,W,C] channel-slice view -> [H*W, C] strided rows view."""
+    _, H, W, C = t.shape
+    return t.as_strided((H * W, C), (t.stride(2), 1), t.storage_offset())
