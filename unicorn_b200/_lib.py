@@ -49,7 +49,12 @@ def lib():
     return _lib
 
 
-def check(rc, what=""):
+LAUNCHES = 0  # kernels launched through the C ABI (claimed count for bench.py's gpu_launches)
+
+
+def check(rc, what="", n=1):
+    global LAUNCHES
+    LAUNCHES += n
     if rc != 0:
         msg = lib().uc_last_error().decode("utf-8", "replace")
         raise UnicornB200Error(f"{what} failed (code {rc}): {msg}")

@@ -307,7 +307,7 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   if (d->res && (d->ldres % 8 || d->y_dtype == UC_F32)) return set_error(UC_EINVAL, "uc_conv2d: residual needs 16-bit y, ldres%%8==0");
   if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->w) | reinterpret_cast<uintptr_t>(d->y)) & 15)
     return set_error(UC_EINVAL, "uc_conv2d: pointers must be 16-byte aligned");
-  if (d->gn_stats && (d->gn_groups <= 0 || d->Cout % d->gn_groups || (d->Cout / d->gn_groups) % 4))
+  if (d->gn_stats && (d->gn_groups <= 0 || d->Cout % d->gn_groups))
     return set_error(UC_EINVAL, "uc_conv2d: bad GroupNorm grouping");
   int rc = ensure_driver();
   if (rc) return rc;

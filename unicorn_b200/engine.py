@@ -59,7 +59,7 @@ class UnicornEngine:
         for i in range(1, 4):
             P[f"down{i}"] = (f(b + f"downsample_layers.{i}.0.weight"), f(b + f"downsample_layers.{i}.0.bias"),
                              pw(b + f"downsample_layers.{i}.1.weight"), f(b + f"downsample_layers.{i}.1.bias"))
-            P[f"norm{i}"] = (f(b + f"norm{i}.weight"), f(b + f"norm{i}.bias"))
+            P[f"outnorm{i}"] = (f(b + f"norm{i}.weight"), f(b + f"norm{i}.bias"))
 
         def block(p):
             return dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
@@ -192,7 +192,7 @@ class UnicornEngine:
             for j, bp in enumerate(P["stages"][i]):
                 self.convnext_block(x, bp, f"{tag}.s{i}")
             if i >= 1:
-                nw, nb = P[f"norm{i}"]
+                nw, nb = P[f"outnorm{i}"]
                 Bx, Hx, Wx, Cx = x.shape
                 dst = {1: cat_p3[..., d[1]:], 2: cat_p4[..., d[2]:], 3: self.buf(tag + ".x0n", (1, h32, w32, d[3]))}[i]
                 ops.layernorm(x.view(-1, Cx), nw, nb, 1e-6, out=_rows(dst))
@@ -210,6 +210,8 @@ class UnicornEngine:
         pan_out1 = self.csp(cat_n3, P["C3_n3"], self.buf(tag + ".pan_out1", (1, h16, w16, d[2])), tag + ".C3_n3")
         self.conv_gn(pan_out1, P["bu_conv1"], cat_n4[..., :d[2]])
         pan_out0 = self.csp(cat_n4, P["C3_n4"], self.buf(tag + ".pan_out0", (1, h32, w32, d[3])), tag + ".C3_n4")
+        self.dbg = dict(x2n=x2n, x1n=x1n, x0n=x0n, fpn_out0=fpn_out0, f_out0=f_out0, fpn_out1=fpn_out1, pan_out2=pan_out2,
+                        pan_out1=pan_out1, pan_out0=pan_out0)
         return (pan_out2, pan_out1, pan_out0), {"feat": x1n, "h": h16, "w": w16}
 
     # ------------------------------------------------------------------------------------------ interaction
