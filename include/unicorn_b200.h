@@ -80,8 +80,9 @@ typedef struct UcConv2d {
   int y_dtype;
   int block_n; /* 0 = auto; else force the N tile (16,32,64,96,128,192,256) */
   /* Optional GroupNorm statistics of the (pre-activation) output, accumulated per (image, group):
-   * gn_stats[b][g] = {sum, sumsq}; must be zeroed by the caller; NULL = off. */
-  float* gn_stats;
+   * gn_stats[b][g] = {sum, sumsq} as int64 fixed point (value * 2^22; integer atomics => order independent,
+   * bit-reproducible); must be zeroed by the caller; NULL = off.  Consumed by uc_groupnorm_apply. */
+  void* gn_stats;
   int gn_groups;
 } UcConv2d;
 UC_API int uc_conv2d(const UcConv2d* d, void* stream);
@@ -105,7 +106,7 @@ UC_API int uc_layernorm(const void* x, int ldx, const void* res, int ldres, cons
  * y = act((x-mean)*rstd*w+b) [+ prior[pix]*beta[c]] ; optional second output y2 = y + add2.
  * network_blocks.py:50-51 with exp/unicorn_track.py:450-470 (GN16, eps 1e-3, SiLU); unicorn.py:38 (GN32, eps 1e-5);
  * unicorn_head.py:272-275 (prior fusion).  x,y,add2,y2 bf16 NHWC with pixel strides. */
-UC_API int uc_groupnorm_apply(const void* x, int ldx, const float* stats, const float* w, const float* b, void* y,
+UC_API int uc_groupnorm_apply(const void* x, int ldx, const void* stats, const float* w, const float* b, void* y,
                               int ldy, int B, long HW, int C, int G, float eps, int act, const float* prior,
                               const float* beta, const void* add2, int ldadd2, void* y2, int ldy2, void* stream);
 

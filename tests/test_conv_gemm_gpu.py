@@ -54,7 +54,7 @@ def test_conv(case):
         xin = big[..., 32:32 + Cin]
         obig = torch.full((B, Ho, Wo, Cout + 64), 7.0, device=dev, dtype=dt)
         out = obig[..., 8:8 + Cout]
-    gn_stats = torch.zeros(B, ex["gn"], 2, device=dev) if ex.get("gn") else None
+    gn_stats = torch.zeros(B, ex["gn"], 2, device=dev, dtype=torch.int64) if ex.get("gn") else None
     act = ex.get("act")
     y = ops.conv2d(xin, wp, K, K, s, pad, bias=bias, act=getattr(ops, "ACT_" + act.upper()) if act else 0,
                    gamma=gamma, res=res, out=out, out_dtype=torch.float32 if ex.get("out_f32") else None,
@@ -82,5 +82,6 @@ def test_conv(case):
         pg = pre.reshape(B, G, Cout // G, Ho * Wo)
         s1 = pg.sum(dim=(2, 3))
         s2 = (pg * pg).sum(dim=(2, 3))
-        assert torch.allclose(gn_stats[..., 0], s1, rtol=2e-3, atol=2e-1), (gn_stats[..., 0], s1)
-        assert torch.allclose(gn_stats[..., 1], s2, rtol=2e-3, atol=2e-1), (gn_stats[..., 1], s2)
+        st = gn_stats.double() / 2 ** 22
+        assert torch.allclose(st[..., 0].float(), s1, rtol=2e-3, atol=2e-1), (st[..., 0], s1)
+        assert torch.allclose(st[..., 1].float(), s2, rtol=2e-3, atol=2e-1), (st[..., 1], s2)

@@ -86,9 +86,13 @@ def test_detections_vs_oracle(setup):
     ref = setup["st"]["dets"]
     assert n > 0 and ref is not None
     assert abs(n - ref.shape[0]) <= max(5, 0.05 * ref.shape[0]), (n, ref.shape[0])
-    iou = orc.box_iou_np(dets[:1, :4].numpy(), ref[:3, :4].numpy())
-    assert iou.max() > 0.9, iou
-    assert abs(float(dets[0, 4] * dets[0, 5]) - float(ref[0, 4] * ref[0, 5])) < 3e-2
+    # every reported top detection must exist in the oracle's list: same box (IoU > 0.7) with score within 3e-2
+    iou = orc.box_iou_np(dets[:, :4].numpy(), ref[:, :4].numpy())
+    j = iou.argmax(1)
+    assert (iou.max(1) > 0.7).all(), iou.max(1)
+    sc = (dets[:, 4] * dets[:, 5]).numpy()
+    sr = (ref[:, 4] * ref[:, 5]).numpy()[j]
+    assert np.abs(sc - sr).max() < 3e-2, (sc, sr)
 
 
 def test_postprocess_exact_on_oracle_head(setup):
@@ -112,7 +116,6 @@ def test_cuda_graph_replay_matches_eager(setup):
     g.initialize_tensor(frames[0:1], boxes[0, 0])
     d1, n1 = g.track_tensor(frames[1:2].pin_memory())
     d2, n2 = g.track_tensor(frames[2:3].pin_memory())
-    # GroupNorm statistics are accumulated with fp32 atomics (order varies run to run at the 1e-7 level), so a
-    # borderline candidate may flip: counts within 2, top detections equal to 1e-2 px / 2e-3 score.
-    assert abs(n2 - setup["n"]) <= 2, (n2, setup["n"])
-    assert torch.allclose(d2[:1], setup["dets"][:1], rtol=0, atol=1e-2), (d2, setup["dets"])
+    # every kernel is deterministic (GroupNorm statistics use integer atomics): graph replay == eager, bit for bit
+    assert n2 == setup["n"], (n2, setup["n"])
+    assert torch.equal(d2, setup["dets"]), (d2, setup["dets"])

@@ -68,7 +68,7 @@ def test_conv_gn_silu_prior():
     w = (torch.randn(C, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev)
     gw, gb, beta = (torch.randn(C, generator=g).to(dev) for _ in range(3))
     prior = torch.rand(B, H, W, generator=g).to(dev)
-    stats = torch.zeros(B, 16, 2, device=dev)
+    stats = torch.zeros(B, 16, 2, device=dev, dtype=torch.int64)
     y = ops.conv2d(x, ops.pack_conv_weight(w), 1, 1, gn_stats=stats, gn_groups=16)
     pos = torch.randn(B, H, W, C, generator=g).to(dev).bfloat16()
     q = torch.empty_like(y)

@@ -41,7 +41,7 @@ struct alignas(64) ConvKernelParams {
   int ldres;
   void* y;
   int ldy, y_dtype, act;
-  float* gn_stats;
+  long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
 
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
                 ss += __shfl_xor_sync(0xffffffffu, ss, o);
               }
               if (lane == 0) {
-                float* dst = p.gn_stats + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
-                atomicAdd(dst, s);
-                atomicAdd(dst + 1, ss);
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
+                atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s * kGnFixedScale)));
+                atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(ss * kGnFixedScale)));
               }
               gs_sum = 0.f; gs_sq = 0.f; gs_left = p.gn_gs; ++gs_group;
             }
@@ -386,7 +386,7 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res; p.ldres = d->ldres;
   p.y = d->y; p.ldy = d->ldy; p.y_dtype = d->y_dtype; p.act = d->act;
-  p.gn_stats = d->gn_stats; p.gn_groups = d->gn_groups;
+  p.gn_stats = static_cast<long long*>(d->gn_stats); p.gn_groups = d->gn_groups;
   p.gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 1 << 30;
   if (d->gn_stats && (bn % p.gn_gs) != 0)
     return set_error(UC_EINVAL, "uc_conv2d: N tile %d incompatible with GroupNorm group size %d", bn, p.gn_gs);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
 // y = act((x - mean_g) * rstd_g * w[c] + b[c]) (+ prior[pix] * beta[c]) (+ y2 written as y + add2).
 // stats [B][G][2] = {sum, sumsq} over (HW x C/G) accumulated by uc_conv2d.  x/y bf16 NHWC (strided); 8 channels / thread.
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __restrict__ x, int ldx,
-                                                               const float* __restrict__ stats, const float* __restrict__ w,
+                                                               const long long* __restrict__ stats, const float* __restrict__ w,
                                                                const float* __restrict__ bvec, uint16_t* __restrict__ y, int ldy,
                                                                int B, long HW, int C, int G, float eps, int act,
                                                                const float* __restrict__ prior, const float* __restrict__ beta,
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
   const int C8 = C >> 3;
   const long total = static_cast<long>(B) * HW * C8;
   const int gs = C / G;
-  const float inv_n = 1.f / (static_cast<float>(HW) * gs);
+  const double inv_n = 1.0 / (static_cast<double>(HW) * gs);
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>(i % C8) * 8;
     const long pix = i / C8;
@@ -252,9 +252,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       const int g = c / gs;
-      const float sum = __ldg(stats + (static_cast<long>(b) * G + g) * 2), sq = __ldg(stats + (static_cast<long>(b) * G + g) * 2 + 1);
-      const float mean = sum * inv_n;
-      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      const double sum = static_cast<double>(__ldg(stats + (static_cast<long>(b) * G + g) * 2)) * (1.0 / kGnFixedScale);
+      const double sq = static_cast<double>(__ldg(stats + (static_cast<long>(b) * G + g) * 2 + 1)) * (1.0 / kGnFixedScale);
+      const double dmean = sum * inv_n;
+      const float mean = static_cast<float>(dmean);
+      const float var = fmaxf(static_cast<float>(sq * inv_n - dmean * dmean), 0.f);
       float v = (f[j] - mean) * rsqrtf(var + eps) * __ldg(w + c) + __ldg(bvec + c);
       if (act == UC_ACT_SILU) v = v / (1.f + __expf(-v));
       else if (act == UC_ACT_RELU) v = fmaxf(v, 0.f);
@@ -331,7 +333,7 @@ extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, 
   return check_launch("uc_layernorm");
 }
 
-extern "C" int uc_groupnorm_apply(const void* x, int ldx, const float* stats, const float* w, const float* b, void* y,
+extern "C" int uc_groupnorm_apply(const void* x, int ldx, const void* stats, const float* w, const float* b, void* y,
                                   int ldy, int B, long HW, int C, int G, float eps, int act, const float* prior,
                                   const float* beta, const void* add2, int ldadd2, void* y2, int ldy2, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -341,7 +343,7 @@ extern "C" int uc_groupnorm_apply(const void* x, int ldx, const float* stats, co
   if (y2 && (!add2 || ldadd2 % 8 || ldy2 % 8)) return set_error(UC_EINVAL, "uc_groupnorm_apply: bad second output");
   const long total = static_cast<long>(B) * HW * (C / 8);
   const int grid = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16));
-  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx, stats, w, b,
+  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx, reinterpret_cast<const long long*>(stats), w, b,
                                                    static_cast<uint16_t*>(y), ldy, B, HW, C, G, eps, act, prior, beta,
                                                    static_cast<const uint16_t*>(add2), ldadd2, static_cast<uint16_t*>(y2), ldy2);
   return check_launch("uc_groupnorm_apply");

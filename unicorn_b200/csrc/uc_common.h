@@ -18,6 +18,10 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
 int check_launch(const char* what);
 int num_sms();
 
+// GroupNorm statistics are accumulated as 64-bit fixed point (value * 2^22) with integer atomics so that the result
+// does not depend on the order in which CTAs finish (bit-reproducible frames).
+constexpr float kGnFixedScale = 4194304.f;
+
 // device ----------------------------------------------------------------------------------------
 #define UC_DT_BF16 0
 #define UC_DT_F32 1

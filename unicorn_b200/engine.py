@@ -128,7 +128,7 @@ class UnicornEngine:
     def begin_frame(self):
         """Zero the GroupNorm statistics arena (one memset per frame; slots are handed out in call order)."""
         if self._stats_arena is None:
-            self._stats_arena = torch.zeros(512, 32, 2, dtype=F32, device=self.dev)
+            self._stats_arena = torch.zeros(512, 32, 2, dtype=torch.int64, device=self.dev)
         else:
             self._stats_arena.zero_()
         self._stats_used = 0
