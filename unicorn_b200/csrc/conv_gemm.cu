@@ -30,6 +30,7 @@ struct ConvTap {
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmC;  // output map for the TMA store (16-bit outputs)
   ConvTap taps[kMaxTaps];
   int ntaps, kchunks;
   int tile_w, tile_h, tiles_w, tiles_h;
@@ -40,7 +41,7 @@ struct alignas(64) ConvKernelParams {
   const void* res;
   int ldres;
   void* y;
-  int ldy, y_dtype, act;
+  int ldy, y_dtype, act, tma_store;
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
           for (int j = 0; j < 32; j += 4) {
             if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           }
-        } else {
+        } else if (!p.tma_store) {
           uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -244,7 +245,33 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
           }
         }
       }
+      if (p.tma_store) {
+        // Stage the tile in shared memory (the operand ring is idle: every MMA has completed) in the 128B-swizzled
+        // layout of a TMA box, 64 channels per block, and let the TMA engine write full lines; it also clips the
+        // out-of-range rows / channels of edge tiles.
+        uint8_t* sC = sA + (c0 >> 6) * kABytes;
+        const int kb = (c0 & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
+          o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
+          o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
+          o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
+          *reinterpret_cast<uint4*>(sC + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
+        }
+        const int limit = min(BLOCK_N, p.Cout - n0);
+        if ((c0 & 63) == 32 || c0 + 32 >= limit) {
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            tma_store_4d(&p.tmC, sC, n0 + (c0 & ~63), ow0, oh0, b);
+            tma_store_commit();
+          }
+        }
+      }
     }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -381,6 +408,17 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
     uint32_t box[3] = {static_cast<uint32_t>(kBlockK), 1, static_cast<uint32_t>(bn)};
     rc = encode_tmap(&p.tmB, dt, 3, d->w, dims, strides, box);
     if (rc) return rc;
+  }
+  p.tma_store = 0;
+  if (d->y_dtype != UC_F32 && (bn % 64) == 0) {  // every 64-channel store box must lie inside this CTA's N tile
+    const CUtensorMapDataType dty = d->y_dtype == UC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho), static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(d->ldy) * es, static_cast<uint64_t>(p.Wo) * d->ldy * es,
+                           static_cast<uint64_t>(p.Ho) * p.Wo * d->ldy * es};
+    uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+    rc = encode_tmap(&p.tmC, dty, 4, d->y, dims, strides, box);
+    if (rc) return rc;
+    p.tma_store = 1;
   }
   p.Cout = d->Cout;
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restr
 
 // ------------------------------------------------------------------------------------------------ LayerNorm rows
 // y[m, :] = LN(x[m, :] (+ r[m, :])) * w + b, one warp per row, C <= 2048, C even.  x/r/y 16-bit rows with strides.
+template <int MAXI>  // bf16 pairs per lane: C <= 64 * MAXI
 __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restrict__ x, int ldx,
                                                          const uint16_t* __restrict__ r, int ldr,
                                                          const float* __restrict__ w, const float* __restrict__ bvec,
@@ -186,7 +187,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
   const int lane = threadIdx.x & 31;
   const long m = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
-  constexpr int MAXI = 32;  // pairs per lane -> C <= 2048
   float v0[MAXI], v1[MAXI];
   const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + m * ldx);
   const uint32_t* rr = r ? reinterpret_cast<const uint32_t*>(r + m * ldr) : nullptr;
@@ -225,23 +225,38 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm apply
-// y = act((x - mean_g) * rstd_g * w[c] + b[c]) (+ prior[pix] * beta[c]) (+ y2 written as y + add2).
-// stats [B][G][2] = {sum, sumsq} over (HW x C/G) accumulated by uc_conv2d.  x/y bf16 NHWC (strided); 8 channels / thread.
+// y = act(x * scale[c] + shift[c]) (+ prior[pix] * beta[c]); optional second output y2 = y + add2.
+// scale/shift fold the group statistics (int64 fixed point {sum, sumsq} accumulated by uc_conv2d) with the affine
+// parameters; they are computed once per block into shared memory.  x/y bf16 NHWC (strided); 8 channels / thread.
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __restrict__ x, int ldx,
                                                                const long long* __restrict__ stats, const float* __restrict__ w,
                                                                const float* __restrict__ bvec, uint16_t* __restrict__ y, int ldy,
-                                                               int B, long HW, int C, int G, float eps, int act,
+                                                               long HW, int C, int G, float eps, int act,
                                                                const float* __restrict__ prior, const float* __restrict__ beta,
                                                                const uint16_t* __restrict__ add2, int ldadd2,
                                                                uint16_t* __restrict__ y2, int ldy2) {
-  const int C8 = C >> 3;
-  const long total = static_cast<long>(B) * HW * C8;
+  extern __shared__ float sc[];  // [2][C] scale, shift (+ [C] beta)
+  const int b = blockIdx.y;
   const int gs = C / G;
   const double inv_n = 1.0 / (static_cast<double>(HW) * gs);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const double sum = static_cast<double>(stats[(static_cast<long>(b) * G + g) * 2]) * (1.0 / kGnFixedScale);
+    const double sq = static_cast<double>(stats[(static_cast<long>(b) * G + g) * 2 + 1]) * (1.0 / kGnFixedScale);
+    const double mean = sum * inv_n;
+    const float var = fmaxf(static_cast<float>(sq * inv_n - mean * mean), 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = rstd * w[c];
+    sc[c] = a;
+    sc[C + c] = bvec[c] - static_cast<float>(mean) * a;
+    sc[2 * C + c] = beta ? beta[c] : 0.f;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long total = HW * C8;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>(i % C8) * 8;
-    const long pix = i / C8;
-    const int b = static_cast<int>(pix / HW);
+    const long pix = static_cast<long>(b) * HW + i / C8;
     const uint4 u = *reinterpret_cast<const uint4*>(x + pix * ldx + c0);
     const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
     float f[8];
@@ -250,18 +265,10 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
     const float pr = prior ? __ldg(prior + pix) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const int g = c / gs;
-      const double sum = static_cast<double>(__ldg(stats + (static_cast<long>(b) * G + g) * 2)) * (1.0 / kGnFixedScale);
-      const double sq = static_cast<double>(__ldg(stats + (static_cast<long>(b) * G + g) * 2 + 1)) * (1.0 / kGnFixedScale);
-      const double dmean = sum * inv_n;
-      const float mean = static_cast<float>(dmean);
-      const float var = fmaxf(static_cast<float>(sq * inv_n - dmean * dmean), 0.f);
-      float v = (f[j] - mean) * rsqrtf(var + eps) * __ldg(w + c) + __ldg(bvec + c);
+      float v = fmaf(f[j], sc[c0 + j], sc[C + c0 + j]);
       if (act == UC_ACT_SILU) v = v / (1.f + __expf(-v));
       else if (act == UC_ACT_RELU) v = fmaxf(v, 0.f);
-      if (prior) v += pr * __ldg(beta + c);
-      f[j] = v;
+      f[j] = fmaf(pr, sc[2 * C + c0 + j], v);
     }
     uint4 o;
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
@@ -327,9 +334,16 @@ extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, 
   if (C % 2 || C > 2048 || ldx % 2 || ldy % 2 || (res && ldres % 2)) return set_error(UC_EINVAL, "uc_layernorm: C even <= 2048, even strides");
   if (dtype != UC_BF16 && dtype != UC_F16) return set_error(UC_EINVAL, "uc_layernorm: 16-bit dtypes only");
   const long blocks = (M + 7) / 8;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx,
-                                                                      static_cast<const uint16_t*>(res), ldres, w, b,
-                                                                      static_cast<uint16_t*>(y), ldy, M, C, eps, dtype);
+#define UC_LN(MAXI)                                                                                                      \
+  layernorm_kernel<MAXI><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(                                            \
+      static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(res), ldres, w, b, static_cast<uint16_t*>(y), ldy, M, C, eps, dtype)
+  if (C <= 128) UC_LN(2);
+  else if (C <= 256) UC_LN(4);
+  else if (C <= 384) UC_LN(6);
+  else if (C <= 768) UC_LN(12);
+  else if (C <= 1536) UC_LN(24);
+  else UC_LN(32);
+#undef UC_LN
   return check_launch("uc_layernorm");
 }
 
@@ -341,10 +355,12 @@ extern "C" int uc_groupnorm_apply(const void* x, int ldx, const void* stats, con
   if (C % 8 || ldx % 8 || ldy % 8 || C % G) return set_error(UC_EINVAL, "uc_groupnorm_apply: C, ldx, ldy multiples of 8; C %% G == 0");
   if ((prior != nullptr) != (beta != nullptr)) return set_error(UC_EINVAL, "uc_groupnorm_apply: prior and beta go together");
   if (y2 && (!add2 || ldadd2 % 8 || ldy2 % 8)) return set_error(UC_EINVAL, "uc_groupnorm_apply: bad second output");
-  const long total = static_cast<long>(B) * HW * (C / 8);
-  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16));
-  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), ldx, reinterpret_cast<const long long*>(stats), w, b,
-                                                   static_cast<uint16_t*>(y), ldy, B, HW, C, G, eps, act, prior, beta,
-                                                   static_cast<const uint16_t*>(add2), ldadd2, static_cast<uint16_t*>(y2), ldy2);
+  const long total = HW * (C / 8);
+  // each block pays C scale/shift computations up front: give every block >= 16 elements per thread
+  const int gx = static_cast<int>(std::max<long>(1, std::min<long>((total + 256 * 16 - 1) / (256 * 16), static_cast<long>(num_sms()) * 4)));
+  if (C > 4096) return set_error(UC_EINVAL, "uc_groupnorm_apply: C too large");
+  groupnorm_apply_kernel<<<dim3(gx, B), 256, 3 * C * sizeof(float), stream>>>(
+      static_cast<const uint16_t*>(x), ldx, reinterpret_cast<const long long*>(stats), w, b, static_cast<uint16_t*>(y), ldy, HW, C, G,
+      eps, act, prior, beta, static_cast<const uint16_t*>(add2), ldadd2, static_cast<uint16_t*>(y2), ldy2);
   return check_launch("uc_groupnorm_apply");
 }

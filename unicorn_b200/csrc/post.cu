@@ -130,93 +130,120 @@ __global__ void __launch_bounds__(256) det_gather_kernel(const float* __restrict
   }
 }
 
-// ---- suppression bit matrix: mask[i][w] bit j set iff j=64w+bit > i, same class, IoU(i,j) > thr
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sorted, const int* __restrict__ count, float thr,
-                                                       unsigned long long* __restrict__ mask, int words_cap) {
-  const int n = *count;
-  const int nb = (n + 63) / 64;
-  const int rb = blockIdx.y, cb = blockIdx.x;
-  if (rb >= nb || cb >= nb || cb < rb) return;
-  __shared__ float cbx[64][5];
-  const int cj = cb * 64 + threadIdx.x;
-  if (cj < n) {
-    const float* d = sorted + static_cast<long>(cj) * 7;
-    cbx[threadIdx.x][0] = d[0]; cbx[threadIdx.x][1] = d[1]; cbx[threadIdx.x][2] = d[2]; cbx[threadIdx.x][3] = d[3];
-    cbx[threadIdx.x][4] = d[6];
-  }
-  __syncthreads();
-  const int i = rb * 64 + threadIdx.x;
-  if (i >= n) return;
-  const float* d = sorted + static_cast<long>(i) * 7;
-  const float x1 = d[0], y1 = d[1], x2 = d[2], y2 = d[3], cls = d[6];
-  const float area = (x2 - x1) * (y2 - y1);
-  unsigned long long bits = 0ull;
-  const int lim = min(64, n - cb * 64);
-  for (int t = (rb == cb ? threadIdx.x + 1 : 0); t < lim; ++t) {
-    if (cbx[t][4] != cls) continue;
-    const float xx1 = fmaxf(x1, cbx[t][0]), yy1 = fmaxf(y1, cbx[t][1]);
-    const float xx2 = fminf(x2, cbx[t][2]), yy2 = fminf(y2, cbx[t][3]);
-    const float w = fmaxf(xx2 - xx1, 0.f), h = fmaxf(yy2 - yy1, 0.f);
-    const float inter = w * h;
-    const float areab = (cbx[t][2] - cbx[t][0]) * (cbx[t][3] - cbx[t][1]);
-    const float iou = inter / (area + areab - inter);
-    if (iou > thr) bits |= 1ull << t;
-  }
-  mask[static_cast<long>(i) * words_cap + cb] = bits;
+// ---- greedy NMS without an N x N matrix (one CTA).  Candidates are visited in score order in chunks of 256:
+//  1. every candidate of the chunk is tested against the boxes kept so far (4 threads per candidate split the list);
+//  2. the survivors of the chunk are tested against each other (256 x 256 bits in shared memory);
+//  3. one warp resolves the chunk greedily, jumping from survivor to survivor with ffs;
+//  4. the newly kept boxes are appended to the kept list (shared memory, spilling to the output rows in global).
+// Work ~ N x kept IoUs instead of N^2, and the sequential part is proportional to the number of kept boxes.
+// IoU arithmetic is torchvision's devIoU (fp32, inter / (areaA + areaB - inter) > thr), same-class pairs only.
+constexpr int kNmsChunk = 256;
+constexpr int kNmsKeepSmem = 3072;
+
+__device__ __forceinline__ bool nms_hit(const float4 a, const float4 b, float thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(xx2 - xx1, 0.f), h = fmaxf(yy2 - yy1, 0.f);
+  const float inter = w * h;
+  const float sa = (a.z - a.x) * (a.w - a.y), sb = (b.z - b.x) * (b.w - b.y);
+  return inter / (sa + sb - inter) > thr;
 }
 
-// ---- greedy scan over the sorted boxes (one CTA).  Work is proportional to the number of KEPT boxes:
-// inside a 64-box block the next survivor is found with ffs on the running removed-word.
-__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ count,
-                                                         int words_cap, const float* __restrict__ sorted, float* __restrict__ out,
-                                                         int* __restrict__ out_count) {
-  extern __shared__ unsigned long long removed[];  // [words]
-  __shared__ unsigned long long kept_bits;
-  __shared__ int n_out;
+__global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restrict__ sorted, const int* __restrict__ count, float thr,
+                                                           float* __restrict__ out, int* __restrict__ out_count) {
+  extern __shared__ float4 kept_box[];                       // [kNmsKeepSmem]
+  float* kept_cls = reinterpret_cast<float*>(kept_box + kNmsKeepSmem);  // [kNmsKeepSmem]
+  __shared__ float4 cbox[kNmsChunk];
+  __shared__ float ccls[kNmsChunk];
+  __shared__ unsigned long long pair_mask[kNmsChunk][4];
+  __shared__ unsigned long long alive_w[4], kept_w[4];
+  __shared__ int nk_s;
   const int n = *count;
-  const int nb = (n + 63) / 64;
-  for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0ull;
-  if (threadIdx.x == 0) n_out = 0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) nk_s = 0;
   __syncthreads();
-  for (int b = 0; b < nb; ++b) {
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      const int i0 = b * 64 + lane, i1 = i0 + 32;
-      const unsigned long long d0 = i0 < n ? mask[static_cast<long>(i0) * words_cap + b] : 0ull;
-      const unsigned long long d1 = i1 < n ? mask[static_cast<long>(i1) * words_cap + b] : 0ull;
-      unsigned long long cur = removed[b];
-      if (n - b * 64 < 64) cur |= ~0ull << (n - b * 64);
-      unsigned long long kept = 0ull;
-      while (~cur != 0ull) {
-        const int t = __ffsll(static_cast<long long>(~cur)) - 1;
-        kept |= 1ull << t;
-        const unsigned long long dl = __shfl_sync(0xffffffffu, t < 32 ? d0 : d1, t & 31);
-        cur |= dl | (1ull << t);
-      }
-      if (lane == 0) kept_bits = kept;
+  for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
+    const int nk = nk_s;
+    const int ci = tid >> 2, sub = tid & 3;  // candidate within chunk, quarter of the kept list
+    const int j = c0 + ci;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cl = -1.f;
+    if (j < n) {
+      const float* d = sorted + static_cast<long>(j) * 7;
+      bx = make_float4(d[0], d[1], d[2], d[3]);
+      cl = d[6];
+    }
+    bool sup = (j >= n);
+    for (int k = sub; k < nk && !sup; k += 4) {
+      float4 kb;
+      float kc;
+      if (k < kNmsKeepSmem) { kb = kept_box[k]; kc = kept_cls[k]; }
+      else { const float* d = out + static_cast<long>(k) * 7; kb = make_float4(d[0], d[1], d[2], d[3]); kc = d[6]; }
+      if (kc == cl && nms_hit(kb, bx, thr)) sup = true;
+    }
+    sup |= __shfl_xor_sync(0xffffffffu, sup, 1) != 0;
+    sup |= __shfl_xor_sync(0xffffffffu, sup, 2) != 0;
+    if (sub == 0) { cbox[ci] = bx; ccls[ci] = cl; }
+    // alive words: ballot over lanes with sub == 0 (8 candidates per warp)
+    const unsigned bal = __ballot_sync(0xffffffffu, !sup && sub == 0);
+    if (tid < 4) alive_w[tid] = 0ull;
+    __syncthreads();
+    if (lane == 0) {
+      // compress ballot bits (every 4th lane) into 8 bits at position (warp*8)
+      unsigned v = 0;
+      for (int t = 0; t < 8; ++t) v |= ((bal >> (4 * t)) & 1u) << t;
+      const int cbase = (tid >> 5) * 8;  // first candidate of this warp
+      atomicOr(&alive_w[cbase >> 6], static_cast<unsigned long long>(v) << (cbase & 63));
     }
     __syncthreads();
-    unsigned long long kb = kept_bits;
-    const int base_out = n_out;
-    const int nk = __popcll(kb);
-    // OR the kept rows into the removed vector (words > b) and emit the kept rows
-    int ord = 0;
-    while (kb) {
-      const int t = __ffsll(static_cast<long long>(kb)) - 1;
-      kb &= kb - 1;
-      const long i = static_cast<long>(b) * 64 + t;
-      for (int w = b + 1 + threadIdx.x; w < nb; w += blockDim.x) {
-        const unsigned long long mw = mask[i * words_cap + w];
-        if (mw) removed[w] |= mw;
+    {  // pairwise bits inside the chunk: candidate ci vs candidates [sub*64, sub*64+64), later ones only
+      unsigned long long bits = 0ull;
+      const bool me = (alive_w[ci >> 6] >> (ci & 63)) & 1ull;
+      if (me) {
+        const unsigned long long aw = alive_w[sub];
+        for (int t = 0; t < 64; ++t) {
+          const int o = sub * 64 + t;
+          if (o > ci && ((aw >> t) & 1ull) && ccls[o] == cl && nms_hit(bx, cbox[o], thr)) bits |= 1ull << t;
+        }
       }
-      if (threadIdx.x < 7) out[static_cast<long>(base_out + ord) * 7 + threadIdx.x] = sorted[i * 7 + threadIdx.x];
-      ++ord;
+      pair_mask[ci][sub] = bits;
     }
     __syncthreads();
-    if (threadIdx.x == 0) n_out = base_out + nk;
+    if (tid < 32) {  // greedy resolution of the chunk (all lanes run the same scalar code)
+      unsigned long long removed[4] = {0ull, 0ull, 0ull, 0ull};
+      unsigned long long kept[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        unsigned long long cur = ~alive_w[w] | removed[w];
+        while (~cur != 0ull) {
+          const int t = __ffsll(static_cast<long long>(~cur)) - 1;
+          kept[w] |= 1ull << t;
+          const int r = w * 64 + t;
+          cur |= pair_mask[r][w] | (1ull << t);
+#pragma unroll
+          for (int w2 = w + 1; w2 < 4; ++w2) removed[w2] |= pair_mask[r][w2];
+        }
+      }
+      if (tid == 0) { kept_w[0] = kept[0]; kept_w[1] = kept[1]; kept_w[2] = kept[2]; kept_w[3] = kept[3]; }
+    }
+    __syncthreads();
+    if (tid < kNmsChunk) {
+      const int w = tid >> 6, t = tid & 63;
+      if ((kept_w[w] >> t) & 1ull) {
+        int pos = nk + __popcll(kept_w[w] & ((1ull << t) - 1ull));
+        for (int w2 = 0; w2 < w; ++w2) pos += __popcll(kept_w[w2]);
+        if (pos < kNmsKeepSmem) { kept_box[pos] = cbox[tid]; kept_cls[pos] = ccls[tid]; }
+        const float* d = sorted + static_cast<long>(c0 + tid) * 7;
+        float* o = out + static_cast<long>(pos) * 7;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) o[q] = d[q];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) nk_s = nk + __popcll(kept_w[0]) + __popcll(kept_w[1]) + __popcll(kept_w[2]) + __popcll(kept_w[3]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out_count = n_out;
+  if (tid == 0) *out_count = nk_s;
 }
 
 }  // namespace uc
@@ -242,8 +269,7 @@ extern "C" long uc_postprocess_workspace_bytes(int max_anchors) {
   const long A = max_anchors;
   long a2 = 1;
   while (a2 < A) a2 <<= 1;
-  const long words = (A + 63) / 64;
-  return A * 7 * 4 * 2 + a2 * 8 + A * words * 8 + 256;
+  return A * 7 * 4 * 2 + a2 * 8 + 256;
 }
 
 extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, void* workspace,
@@ -253,24 +279,20 @@ extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thr
   if (workspace_bytes < uc_postprocess_workspace_bytes(A)) return set_error(UC_EINVAL, "uc_postprocess: workspace too small");
   long a2 = 1;
   while (a2 < A) a2 <<= 1;
-  const int words = (A + 63) / 64;
-  if (words * 8 > 200 * 1024) return set_error(UC_EINVAL, "uc_postprocess: too many anchors (%d)", A);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* count = reinterpret_cast<int*>(ws);
   float* det = reinterpret_cast<float*>(ws + 256);
   float* sorted = det + static_cast<long>(A) * 7;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sorted + static_cast<long>(A) * 7);
-  unsigned long long* mask = keys + a2;
   det_filter_kernel<<<1, 1024, 0, stream>>>(pred, A, ncls, conf_thre, det, keys, count, A);
   sort_desc_kernel<<<1, 1024, 0, stream>>>(keys, count, static_cast<int>(a2));
   det_gather_kernel<<<std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream>>>(det, keys, count, sorted);
-  dim3 g(static_cast<unsigned>(words), static_cast<unsigned>(words));
-  nms_mask_kernel<<<g, 64, 0, stream>>>(sorted, count, nms_thre, mask, words);
+  constexpr int smem = kNmsKeepSmem * (16 + 4);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  nms_scan_kernel<<<1, 1024, static_cast<size_t>(words) * 8, stream>>>(mask, count, words, sorted, out_dets, out_count);
+  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count);
   return check_launch("uc_postprocess");
 }

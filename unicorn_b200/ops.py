@@ -266,5 +266,5 @@ def postprocess_device(pred, ncls, conf, nms, ws):
     A = pred.shape[0]
     assert pred.is_contiguous() and pred.dtype == torch.float32 and A <= ws.max_anchors
     _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
-               "uc_postprocess", 5)
+               "uc_postprocess", 4)
     return ws.dets, ws.count
