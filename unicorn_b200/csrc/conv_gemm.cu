@@ -10,7 +10,7 @@
 // warps read the accumulator back with tcgen05.ld and apply bias / activation / layer-scale+residual, and
 // optionally accumulate GroupNorm statistics, before a vectorised NHWC store.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 // Reference call sites replaced: see include/unicorn_b200.h (uc_conv2d).
 #include "uc_ptx.cuh"
 #include "uc_common.h"
@@ -22,6 +22,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 16-bit elements -> 128-byte rows
 constexpr int kMaxTaps = 9;
 constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 struct ConvTap {
   int16_t map, dw, dh, tap;
@@ -46,18 +47,38 @@ struct alignas(64) ConvKernelParams {
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exact-erf GELU (nn.GELU()) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below the bf16 output ulp):
+// two MUFU ops (rcp, ex2) and ~12 FMAs instead of libdevice erff's long dependent chain — the epilogue warps have
+// nobody to hide latency behind.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = fast_ex2(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case UC_ACT_RELU: return fmaxf(x, 0.f);
-    case UC_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-    case UC_ACT_SILU: return x / (1.f + __expf(-x));
-    case UC_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case UC_ACT_GELU: return gelu_erf(x);
+    case UC_ACT_SILU: return __fdividef(x, 1.f + fast_ex2(-x * 1.4426950408889634f));
+    case UC_ACT_SIGMOID: return __fdividef(1.f, 1.f + fast_ex2(-x * 1.4426950408889634f));
     default: return x;
   }
 }
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -133,141 +154,149 @@ __global__ void __launch_bounds__(192) conv_gemm_kernel(const __grid_constant__ 
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused math -> NHWC global
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // Eight warps: warp w owns TMEM lane quadrant (w & 3) and the 32-column chunks of parity (w - 2) / 4, so that
+    // two warps share each scheduler and hide each other's latencies.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int wi = row % p.tile_w, hi = row / p.tile_w;
     const int ow = ow0 + wi, oh = oh0 + hi;
     const bool valid = (ow < p.Wo) && (oh < p.Ho);
     const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
+    const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    float gs_sum = 0.f, gs_sq = 0.f;
-    int gs_left = p.gn_gs;
-    int gs_group = p.gn_stats ? n0 / p.gn_gs : 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      if (n0 + c0 >= p.Cout) break;
-      uint32_t v[32];
-      if constexpr (BLOCK_N % 32 == 0) {
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      } else {
-        uint32_t h[16];
-        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, h);
+    for (int c64 = 0; c64 < BLOCK_N; c64 += 64) {
+      const int c0 = c64 + half * 32;
+      if (c0 < limit) {
+        uint32_t v[32];
+        if constexpr (BLOCK_N % 32 == 0) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        } else {
+          uint32_t h[16];
+          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, h);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
-      }
-      tmem_ld_wait();
-      const int cbase = n0 + c0;
-      const int ncols = min(32, min(BLOCK_N - c0, p.Cout - cbase));  // multiple of 8
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j < ncols) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-          }
+          for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
         }
-      }
-      if (p.gn_stats) {
+        tmem_ld_wait();
+        const int cbase = n0 + c0;
+        const int ncols = min(32, limit - c0);  // multiple of 8
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < ncols) {
-            const float x = valid ? f[j] : 0.f;
-            gs_sum += x;
-            gs_sq += x * x;
-            if (--gs_left == 0) {
-              float s = gs_sum, ss = gs_sq;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                ss += __shfl_xor_sync(0xffffffffu, ss, o);
-              }
-              if (lane == 0) {
-                unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
-                atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s * kGnFixedScale)));
-                atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(ss * kGnFixedScale)));
-              }
-              gs_sum = 0.f; gs_sq = 0.f; gs_left = p.gn_gs; ++gs_group;
-            }
-          }
-        }
-      }
-      if (p.act != UC_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-      }
-      if (p.gamma) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j < ncols) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
-            f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
-          }
-        }
-      }
-      if (valid) {
-        if (p.res) {
-          const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
-                f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
-              }
-            }
-          }
-        }
-        if (p.y_dtype == UC_F32) {
-          float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-        } else if (!p.tma_store) {
-          uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
             if (j < ncols) {
-              uint4 o;
-              o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
-              o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
-              o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
-              o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
-              *reinterpret_cast<uint4*>(yp + j) = o;
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
             }
           }
         }
-      }
-      if (p.tma_store) {
-        // Stage the tile in shared memory (the operand ring is idle: every MMA has completed) in the 128B-swizzled
-        // layout of a TMA box, 64 channels per block, and let the TMA engine write full lines; it also clips the
-        // out-of-range rows / channels of edge tiles.
-        uint8_t* sC = sA + (c0 >> 6) * kABytes;
-        const int kb = (c0 & 63) >> 3;
+        if (p.gn_stats) {
+          // per-group partial sums of this warp's 32 rows x chunk columns; a group may span several chunks, its
+          // partial sums are simply added by the (order-independent) integer atomics.
+          float gs_sum = 0.f, gs_sq = 0.f;
+          int gs_left = p.gn_gs - (cbase % p.gn_gs);
+          int gs_group = cbase / p.gn_gs;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
-          o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
-          o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
-          o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
-          *reinterpret_cast<uint4*>(sC + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
-        }
-        const int limit = min(BLOCK_N, p.Cout - n0);
-        if ((c0 & 63) == 32 || c0 + 32 >= limit) {
-          fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 2 && lane == 0) {
-            tma_store_4d(&p.tmC, sC, n0 + (c0 & ~63), ow0, oh0, b);
-            tma_store_commit();
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              const float x = valid ? f[j] : 0.f;
+              gs_sum += x;
+              gs_sq += x * x;
+              if (--gs_left == 0 || j == ncols - 1) {
+                float s1 = gs_sum, s2 = gs_sq;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                  s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (lane == 0) {
+                  unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
+                  atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+                  atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
+                }
+                gs_sum = 0.f; gs_sq = 0.f;
+                if (gs_left == 0) { gs_left = p.gn_gs; ++gs_group; }
+              }
+            }
           }
+        }
+        if (p.act != UC_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (p.gamma) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
+              f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
+            }
+          }
+        }
+        if (valid) {
+          if (p.res) {
+            const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+                  f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+                }
+              }
+            }
+          }
+          if (p.y_dtype == UC_F32) {
+            float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          } else if (!p.tma_store) {
+            uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 o;
+                o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
+                o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
+                o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
+                o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
+                *reinterpret_cast<uint4*>(yp + j) = o;
+              }
+            }
+          }
+        }
+        if (p.tma_store) {
+          // Stage the tile in shared memory (the operand ring is idle: every MMA has completed) in the 128B-swizzled
+          // layout of a TMA box, 64 channels per block; the TMA engine then writes full lines and clips the
+          // out-of-range rows / channels of edge tiles.
+          uint8_t* sC = sA + (c64 >> 6) * kABytes;
+          const int kb = half * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
+            o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
+            o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
+            o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
+            *reinterpret_cast<uint4*>(sC + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
+          }
+        }
+      }
+      if (p.tma_store && c64 < limit) {  // uniform over the 8 epilogue warps
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          tma_store_4d(&p.tmC, sA + (c64 >> 6) * kABytes, n0 + c64, ow0, oh0, b);
+          tma_store_commit();
         }
       }
     }
@@ -293,7 +322,7 @@ static int launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t stream
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, stream>>>(p);
+  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d> launch: %s", BLOCK_N, STAGES, cudaGetErrorString(e));
   return UC_OK;
