@@ -97,6 +97,10 @@ UC_API int uc_stem_ln(const float* img, const float* w48, const float* bias, con
 UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias, const float* lnw, const float* lnb,
                          void* y_bf16, int B, int H, int W, int C, float eps, void* stream);
 
+/* Depthwise 7x7 (pad 3)+bias only (shared-memory tiled); follow with uc_layernorm for the ConvNeXt block. */
+UC_API int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
+                      void* stream);
+
 /* Row LayerNorm: y[m,:] = LN(x[m,:] + res[m,:]) * w + b  (res may be NULL).  16-bit rows with element strides.
  * convnext.py:176-184 (downsample / out norms), deformable_transformer.py:113,121,127-130 (post-norm). */
 UC_API int uc_layernorm(const void* x, int ldx, const void* res, int ldres, const float* w, const float* b, void* y,

@@ -1,7 +1,7 @@
 """End-to-end parity of the CUDA engine against the CPU oracle and the golden fixtures (tiny 320x320 SOT frame).
 
 Tolerances (relative to each tensor's max magnitude; the engine computes in bf16 operands / fp32 accumulate, the
-oracle in fp32): neck maps 8e-2, backbone feat 4e-2, interaction / embeddings 5e-2, propagated prior 4e-2 abs,
+oracle in fp32): neck maps 8e-2, backbone feat 4e-2, interaction / embeddings 5e-2, propagated prior 6e-2 abs,
 head: box centre 0.2 grid cells, log(w,h) 0.2, obj/cls probabilities 3e-2 abs."""
 import os
 import sys
@@ -64,7 +64,7 @@ def test_stage_parity_vs_oracle(setup):
     errs["head_score"] = (head[..., 4:] - href[..., 4:]).abs().max().item()
     print("stage errors:", {k: f"{v:.3e}" for k, v in errs.items()})
     tol = dict(fpn0=8e-2, fpn1=8e-2, fpn2=8e-2, feat=4e-2, inter_pre=5e-2, inter_cur=5e-2, embed_pre=5e-2, embed_cur=5e-2,
-               coarse=4e-2, head_xy=0.2, head_logwh=0.2, head_score=3e-2)
+               coarse=6e-2, head_xy=0.2, head_logwh=0.2, head_score=3e-2)
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
     assert not bad, f"out of tolerance: {bad} (all: {errs})"
 
@@ -74,7 +74,7 @@ def test_golden_fixture(setup):
     last = setup["trk"].last
     assert rel(nchw(last["fpn"][2])[0, ::4], torch.from_numpy(g["fpn2"])) < 8e-2
     assert rel(nchw(last["embed_cur"])[0, :, ::4, ::4], torch.from_numpy(g["embed_cur_sub"])) < 5e-2
-    assert (last["priors"][0].cpu() - torch.from_numpy(g["coarse"])[0]).abs().max().item() < 4e-2
+    assert (last["priors"][0].cpu() - torch.from_numpy(g["coarse"])[0]).abs().max().item() < 6e-2
     assert (last["head"].cpu()[..., 4:] - torch.from_numpy(g["head"])[..., 4:]).abs().max().item() < 3e-2
 
 

@@ -45,6 +45,18 @@ def test_dwconv_ln(C, H, W):
     close(out, ref, 6e-3, "dwconv_ln")
 
 
+@pytest.mark.parametrize("C,H,W", [(96, 20, 28), (192, 17, 23), (256, 10, 16), (1536, 5, 9), (384, 33, 40)])
+def test_dwconv_tiled(C, H, W):
+    from unicorn_b200 import ops
+    g = G(21)
+    x = torch.randn(2, H, W, C, generator=g).to(dev).bfloat16()
+    w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    out = ops.dwconv7(x, ops.pack_dw_weight(w), b)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=3, groups=C).permute(0, 2, 3, 1)
+    close(out, ref, 5e-3, "dwconv tiled")
+
+
 @pytest.mark.parametrize("C", [96, 192, 256, 1536])
 def test_layernorm(C):
     from unicorn_b200 import ops

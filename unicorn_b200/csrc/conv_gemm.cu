@@ -329,18 +329,23 @@ static int launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t stream
 }
 
 static int pick_block_n(int Cout, int m_tiles, int gn_gs) {
-  static const int cands[] = {256, 192, 128, 96, 64, 32, 16};
+  // Measured on B200 (tools/bench_conv.py): the 128-wide tile with 3 stages (96 KB) wins or ties everywhere because
+  // two CTAs fit on an SM and one's epilogue overlaps the other's main loop; 96 plays the same role when GroupNorm
+  // groups (12/24/48/96 channels) must not straddle N tiles.  Larger tiles only when they are the only fit.
+  static const int cands[] = {128, 96, 64, 192, 256, 32, 16};
+  const int sms = num_sms();
   int best = 0;
-  long best_cost = -1;
+  double best_cost = -1.0;
   for (int bn : cands) {
     if (gn_gs > 0 && (bn % gn_gs) != 0) continue;  // GroupNorm groups must not straddle N tiles
     const int nt = (Cout + bn - 1) / bn;
     const long waste_cols = static_cast<long>(nt) * bn - Cout;
     if (waste_cols * 8 > Cout && bn > 16 && gn_gs <= 0) continue;  // > 12.5 % padded columns
     const long ctas = static_cast<long>(nt) * m_tiles;
-    // cost model: waves over 148 SMs x per-CTA time (~ bn + fixed overhead equivalent to 48 columns)
-    const long waves = (ctas + 147) / 148;
-    const long cost = waves * (bn + 48);
+    const int per_sm = (bn <= 128) ? 2 : 1;  // resident CTAs per SM (shared memory)
+    const long waves = (ctas + static_cast<long>(sms) * per_sm - 1) / (static_cast<long>(sms) * per_sm);
+    // per-CTA time ~ (bn + 64) with the overlap of co-resident CTAs folded into per_sm
+    const double cost = static_cast<double>(waves) * (bn + 64);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;

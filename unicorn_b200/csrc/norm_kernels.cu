@@ -176,6 +176,74 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dwconv7 (tiled)
+// Depthwise 7x7 (pad 3) + bias on a channel chunk of CCH channels and a TH x 16 output tile staged (with its 3-pixel
+// halo) in shared memory by cp.async; out-of-map halo pixels are zero-filled.  The LayerNorm that follows in the
+// ConvNeXt block runs as uc_layernorm on the (L2-resident) result.  x, y NHWC bf16 [B,H,W,C]; w [49][C] fp32.
+template <int CCH>
+__global__ void __launch_bounds__(256) dwconv7_tiled_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, uint16_t* __restrict__ y, int H,
+                                                             int W, int C, int tiles_w) {
+  constexpr int TW = 16, PAIRS = CCH / 2, TH = 256 / PAIRS, HW_ = TW + 6, HH_ = TH + 6;
+  constexpr int PIX_BYTES = CCH * 2, CHUNKS = PIX_BYTES / 16;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t* tile = dsm;                                             // [HH_][HW_][CCH] bf16
+  float* sw = reinterpret_cast<float*>(dsm + HH_ * HW_ * PIX_BYTES);  // [49][CCH]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * CCH;
+  const int ow0 = (blockIdx.x % tiles_w) * TW, oh0 = (blockIdx.x / tiles_w) * TH;
+  const uint16_t* xb = x + static_cast<long>(b) * H * W * C;
+  for (int i = threadIdx.x; i < HH_ * HW_ * CHUNKS; i += 256) {
+    const int ch = i % CHUNKS, px = i / CHUNKS;
+    const int hx = px % HW_, hy = px / HW_;
+    const int ih = oh0 + hy - 3, iw = ow0 + hx - 3;
+    uint8_t* dst = tile + px * PIX_BYTES + ch * 16;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const uint16_t* src = xb + (static_cast<long>(ih) * W + iw) * C + c0 + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  for (int i = threadIdx.x; i < 49 * CCH; i += 256) sw[i] = __ldg(w + static_cast<long>(i / CCH) * C + c0 + (i % CCH));
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int cp = threadIdx.x % PAIRS, r = threadIdx.x / PAIRS;
+  float a0[TW], a1[TW];
+  {
+    const float b0 = __ldg(bias + c0 + 2 * cp), b1 = __ldg(bias + c0 + 2 * cp + 1);
+#pragma unroll
+    for (int p = 0; p < TW; ++p) { a0[p] = b0; a1[p] = b1; }
+  }
+#pragma unroll 1
+  for (int kh = 0; kh < 7; ++kh) {
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + (r + kh) * HW_ * PIX_BYTES) + cp;
+    float v0[HW_], v1[HW_];
+#pragma unroll
+    for (int j = 0; j < HW_; ++j) {
+      const uint32_t u = rowp[j * (PIX_BYTES / 4)];
+      v0[j] = bf16lo(u); v1[j] = bf16hi(u);
+    }
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      const float2 wv = *reinterpret_cast<const float2*>(sw + (kh * 7 + kw) * CCH + 2 * cp);
+#pragma unroll
+      for (int p = 0; p < TW; ++p) {
+        a0[p] = fmaf(v0[p + kw], wv.x, a0[p]);
+        a1[p] = fmaf(v1[p + kw], wv.y, a1[p]);
+      }
+    }
+  }
+  const int oh = oh0 + r;
+  if (oh < H) {
+    uint32_t* yr = reinterpret_cast<uint32_t*>(y + (static_cast<long>(b) * H + oh) * W * C + c0) + cp;
+#pragma unroll
+    for (int p = 0; p < TW; ++p) {
+      if (ow0 + p < W) yr[static_cast<long>(ow0 + p) * (C / 2)] = pack_bf16(a0[p], a1[p]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm rows
 // y[m, :] = LN(x[m, :] (+ r[m, :])) * w + b, one warp per row, C <= 2048, C even.  x/r/y 16-bit rows with strides.
 template <int MAXI>  // bf16 pairs per lane: C <= 64 * MAXI
@@ -325,6 +393,26 @@ extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* 
       static_cast<const uint32_t*>(x_bf16), reinterpret_cast<const float2*>(w49), reinterpret_cast<const float2*>(bias),
       reinterpret_cast<const float2*>(lnw), reinterpret_cast<const float2*>(lnb), static_cast<uint32_t*>(y_bf16), B, H, W, C2, eps);
   return check_launch("uc_dwconv7_ln");
+}
+
+extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
+                          void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x_bf16 || !w49 || !bias || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7: null pointer");
+  if (C % 32) return set_error(UC_EINVAL, "uc_dwconv7: C must be a multiple of 32");
+  const int tiles_w = (W + 15) / 16;
+  if (C % 64 == 0) {
+    constexpr int smem = (8 + 6) * 22 * 128 + 49 * 64 * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv7_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    dim3 grid(tiles_w * ((H + 7) / 8), C / 64, B);
+    dwconv7_tiled_kernel<64><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+  } else {
+    constexpr int smem = (16 + 6) * 22 * 64 + 49 * 32 * 4;
+    dim3 grid(tiles_w * ((H + 15) / 16), C / 32, B);
+    dwconv7_tiled_kernel<32><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+  }
+  return check_launch("uc_dwconv7");
 }
 
 extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, const float* w, const float* b, void* y,

@@ -150,7 +150,8 @@ class UnicornEngine:
     def convnext_block(self, x, bp, tag):
         """In place on x (NHWC contiguous) — convnext.py:41-54."""
         B, H, W, C = x.shape
-        t = ops.dwconv7_ln(x, bp["dw"], bp["dwb"], bp["lnw"], bp["lnb"], 1e-6, out=self.buf(tag + ".t", x.shape))
+        t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape))
+        ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
         hid = ops.conv2d(t, bp["w1"], 1, 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
         ops.conv2d(hid, bp["w2"], 1, 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
         return x

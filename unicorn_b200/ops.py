@@ -130,6 +130,15 @@ def dwconv7_ln(x, w49, bias, lnw, lnb, eps=1e-6, out=None):
     return out
 
 
+def dwconv7(x, w49, bias, out=None):
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_L().uc_dwconv7(_p(x), _p(w49), _p(bias), _p(out), B, H, W, C, _S()), "uc_dwconv7")
+    return out
+
+
 def layernorm(x2d, w, b, eps, res=None, out=None):
     """rows [M, C] (unit inner stride)."""
     M, C = x2d.shape
