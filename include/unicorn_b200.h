@@ -151,9 +151,11 @@ UC_API int uc_head_decode(const float* const* regobj, const float* const* cls, c
                           int ld_ro, int ld_cls, int ncls, float* out, void* stream);
 
 /* postprocess (utils/boxes.py:33-77) on the device: out_dets f32 [<=A, 7] rows (x1,y1,x2,y2,obj,cls_conf,cls_id)
- * in descending score order, *out_count (device int) = number of rows. */
+ * in descending score order, *out_count (device int) = number of rows.  max_keep > 0 stops the greedy scan once that
+ * many boxes are kept: the rows returned are exactly the first max_keep rows of the full result (the SOT driver only
+ * consumes output[:max_inst], external/lib/test/tracker/unicorn_sot.py:69-70); max_keep <= 0 = no limit. */
 UC_API long uc_postprocess_workspace_bytes(int max_anchors);
-UC_API int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, void* workspace,
+UC_API int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, int max_keep, void* workspace,
                           long workspace_bytes, float* out_dets, int* out_count, void* stream);
 
 #ifdef __cplusplus

@@ -237,3 +237,20 @@ def test_head_decode():
         grid = torch.stack((xv, yv), 2).view(-1, 2).float().to(dev)
         rows.append(torch.cat([(r[:, :2] + grid) * s, torch.exp(r[:, 2:4]) * s, torch.sigmoid(r[:, 4:5]), torch.sigmoid(c[:, :ncls])], 1))
     close(out[0], torch.cat(rows, 0), 1e-6, "decode")
+
+
+def test_postprocess_max_keep_is_a_prefix():
+    from unicorn_b200 import ops
+    g = G(11)
+    A = 6000
+    pred = torch.cat([torch.rand(A, 1, generator=g) * 1280, torch.rand(A, 1, generator=g) * 800, torch.rand(A, 2, generator=g) * 200 + 20,
+                      torch.rand(A, 2, generator=g)], 1).to(dev).contiguous()
+    ws = ops.PostWorkspace(A, dev)
+    full, cnt = ops.postprocess_device(pred, 1, 0.2, 0.65, ws)
+    n_full = int(cnt.item())
+    full = full[:n_full].clone()
+    for k in (1, 3, 300):
+        ws2 = ops.PostWorkspace(A, dev)
+        part, c2 = ops.postprocess_device(pred, 1, 0.2, 0.65, ws2, max_keep=k)
+        assert int(c2.item()) == min(k, n_full)
+        assert torch.equal(part[:min(k, n_full)], full[:min(k, n_full)])

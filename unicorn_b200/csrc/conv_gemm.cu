@@ -12,6 +12,7 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 // Reference call sites replaced: see include/unicorn_b200.h (uc_conv2d).
+#include <algorithm>
 #include "uc_ptx.cuh"
 #include "uc_common.h"
 #include "../../include/unicorn_b200.h"
@@ -22,7 +23,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 16-bit elements -> 128-byte rows
 constexpr int kMaxTaps = 9;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kConvEpiWarps = 16;                       // four per TMEM lane quadrant
+constexpr int kConvThreads = (2 + kConvEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, then the epilogue warps
 
 struct ConvTap {
   int16_t map, dw, dh, tap;
@@ -34,6 +36,7 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap tmC;  // output map for the TMA store (16-bit outputs)
   ConvTap taps[kMaxTaps];
   int ntaps, kchunks;
+  int n_tiles, m_tiles;
   int tile_w, tile_h, tiles_w, tiles_h;
   int Wo, Ho, B, Cout;
   uint32_t idesc;
@@ -77,27 +80,87 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// Epilogue of one 32-column chunk of one tile, specialised on the activation so that the inner loops are branch-free.
+template <int ACT>
+__device__ __forceinline__ void epi_math(float (&f)[32], const ConvKernelParams& p, int cbase, int ncols, bool valid, int b,
+                                         int lane) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+      }
+    }
+  }
+  if (p.gn_stats) {
+    // per-group partial sums of this warp's 32 rows x chunk columns; a group may span several chunks — partial sums
+    // are simply added by the (order-independent) integer atomics.
+    float gs_sum = 0.f, gs_sq = 0.f;
+    int gs_left = p.gn_gs - (cbase % p.gn_gs);
+    int gs_group = cbase / p.gn_gs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        const float x = valid ? f[j] : 0.f;
+        gs_sum += x;
+        gs_sq += x * x;
+        if (--gs_left == 0 || j == ncols - 1) {
+          float s1 = gs_sum, s2 = gs_sq;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
+            atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+            atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
+          }
+          gs_sum = 0.f; gs_sq = 0.f;
+          if (gs_left == 0) { gs_left = p.gn_gs; ++gs_group; }
+        }
+      }
+    }
+  }
+  if (ACT != UC_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ACT);
+  }
+  if (p.gamma) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
+        f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
+      }
+    }
+  }
+}
+
+// Persistent kernel: grid = min(#tiles, resident CTAs); every CTA walks tiles tile = blockIdx.x + i * gridDim.x (N tile
+// fastest, so CTAs running side by side share the activation tile in L2).  The TMEM accumulator is double buffered:
+// the MMA warp fills accumulator (i+1)&1 while the epilogue warps drain accumulator i&1.
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
-  constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  constexpr uint32_t ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr int C_BLOCKS = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;  // 64-channel staging blocks for the TMA store
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * kABytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* sB = sA + STAGES * kABytes;
+  uint8_t* sC = sB + STAGES * B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + C_BLOCKS * kABytes);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int mt = blockIdx.y;
-  const int twi = mt % p.tiles_w;
-  const int thi = (mt / p.tiles_w) % p.tiles_h;
-  const int b = mt / (p.tiles_w * p.tiles_h);
-  const int ow0 = twi * p.tile_w, oh0 = thi * p.tile_h;
-  const int total = p.ntaps * p.kchunks;
+  const int kiters = p.ntaps * p.kchunks;
+  const int num_tiles = p.n_tiles * p.m_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -106,7 +169,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kConvEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -121,186 +187,182 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
-        const ConvTap tp = p.taps[t];
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
-          tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
-          tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * BLOCK_N;
+        const int mt = tile / p.n_tiles;
+        const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
+        const int b = mt / (p.tiles_w * p.tiles_h);
+        for (int t = 0; t < p.ntaps; ++t) {
+          const ConvTap tp = p.taps[t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
+            tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+            tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int it = 0; it < total; ++it) {
-        mbar_wait(&full[stage], phase);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-        const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
-                   (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
+                     (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused math -> NHWC global
-    // Eight warps: warp w owns TMEM lane quadrant (w & 3) and the 32-column chunks of parity (w - 2) / 4, so that
-    // two warps share each scheduler and hide each other's latencies.
+    // kConvEpiWarps warps: warp w owns TMEM lane quadrant (w & 3) and the 32-column chunks ci with ci % 4 == (w-2)/4,
+    // so four warps share each scheduler and hide each other's latencies.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int wi = row % p.tile_w, hi = row / p.tile_w;
-    const int ow = ow0 + wi, oh = oh0 + hi;
-    const bool valid = (ow < p.Wo) && (oh < p.Ho);
-    const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
-    const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      const int mt = tile / p.n_tiles;
+      const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
+      const int b = mt / (p.tiles_w * p.tiles_h);
+      const int ow = ow0 + wi, oh = oh0 + hi;
+      const bool valid = (ow < p.Wo) && (oh < p.Ho);
+      const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
+      const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
+      if (C_BLOCKS > 0 && p.tma_store) {
+        // the staging blocks are about to be overwritten: the previous tile's TMA stores must have read them
+        if (lane == 0 && q == 0 && cg < 2) tma_store_wait_read();  // the two issuing threads (warps 4 and 8)
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c64 = 0; c64 < BLOCK_N; c64 += 64) {
-      const int c0 = c64 + half * 32;
-      if (c0 < limit) {
-        uint32_t v[32];
-        if constexpr (BLOCK_N % 32 == 0) {
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-        } else {
-          uint32_t h[16];
-          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, h);
+      for (int r0 = 0; r0 < BLOCK_N; r0 += 128) {
+        const int c0 = r0 + cg * 32;
+        const bool last_round = (r0 + 128 >= BLOCK_N);
+        if (c0 < limit && c0 < BLOCK_N) {
+          uint32_t v[32];
+          if constexpr (BLOCK_N % 32 == 0) {
+            tmem_ld_32x32(t_acc + c0, v);
+          } else {
+            uint32_t h[16];
+            tmem_ld_32x16(t_acc + c0, h);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
-        }
-        tmem_ld_wait();
-        const int cbase = n0 + c0;
-        const int ncols = min(32, limit - c0);  // multiple of 8
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-            }
+            for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
           }
-        }
-        if (p.gn_stats) {
-          // per-group partial sums of this warp's 32 rows x chunk columns; a group may span several chunks, its
-          // partial sums are simply added by the (order-independent) integer atomics.
-          float gs_sum = 0.f, gs_sq = 0.f;
-          int gs_left = p.gn_gs - (cbase % p.gn_gs);
-          int gs_group = cbase / p.gn_gs;
+          tmem_ld_wait();
+          if (last_round) {  // this warp's last read of the accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          const int cbase = n0 + c0;
+          const int ncols = min(32, limit - c0);  // multiple of 8
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-              const float x = valid ? f[j] : 0.f;
-              gs_sum += x;
-              gs_sq += x * x;
-              if (--gs_left == 0 || j == ncols - 1) {
-                float s1 = gs_sum, s2 = gs_sq;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          switch (p.act) {
+            case UC_ACT_GELU: epi_math<UC_ACT_GELU>(f, p, cbase, ncols, valid, b, lane); break;
+            case UC_ACT_RELU: epi_math<UC_ACT_RELU>(f, p, cbase, ncols, valid, b, lane); break;
+            case UC_ACT_SILU: epi_math<UC_ACT_SILU>(f, p, cbase, ncols, valid, b, lane); break;
+            case UC_ACT_SIGMOID: epi_math<UC_ACT_SIGMOID>(f, p, cbase, ncols, valid, b, lane); break;
+            default: epi_math<UC_ACT_NONE>(f, p, cbase, ncols, valid, b, lane); break;
+          }
+          if (valid) {
+            if (p.res) {
+              const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                  s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+                    f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+                  }
                 }
-                if (lane == 0) {
-                  unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
-                  atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
-                  atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
-                }
-                gs_sum = 0.f; gs_sq = 0.f;
-                if (gs_left == 0) { gs_left = p.gn_gs; ++gs_group; }
               }
             }
-          }
-        }
-        if (p.act != UC_ACT_NONE) {
+            if (p.y_dtype == UC_F32) {
+              float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        }
-        if (p.gamma) {
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              }
+            } else if (!p.tma_store) {
+              uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
-              f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
-            }
-          }
-        }
-        if (valid) {
-          if (p.res) {
-            const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
-                  f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  uint4 o;
+                  o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
+                  o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
+                  o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
+                  o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
+                  *reinterpret_cast<uint4*>(yp + j) = o;
                 }
               }
             }
           }
-          if (p.y_dtype == UC_F32) {
-            float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
+          if (C_BLOCKS > 0 && p.tma_store) {
+            // Stage in shared memory in the 128B-swizzled layout of a TMA box (64 channels per block); the TMA engine
+            // then writes full lines and clips the out-of-range rows / channels of edge tiles.
+            uint8_t* blk = sC + (c0 >> 6) * kABytes;
+            const int kb = (c0 & 32) >> 3;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-          } else if (!p.tma_store) {
-            uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 o;
-                o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
-                o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
-                o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
-                o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
-                *reinterpret_cast<uint4*>(yp + j) = o;
-              }
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
+              o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
+              o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
+              o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
+              *reinterpret_cast<uint4*>(blk + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
             }
           }
+        } else if (last_round) {
+          // nothing to read in the last round (narrow or edge tile): still release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (p.tma_store) {
-          // Stage the tile in shared memory (the operand ring is idle: every MMA has completed) in the 128B-swizzled
-          // layout of a TMA box, 64 channels per block; the TMA engine then writes full lines and clips the
-          // out-of-range rows / channels of edge tiles.
-          uint8_t* sC = sA + (c64 >> 6) * kABytes;
-          const int kb = half * 4;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
-            o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
-            o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
-            o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
-            *reinterpret_cast<uint4*>(sC + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
+        if (C_BLOCKS > 0 && p.tma_store && r0 < limit) {  // uniform over the epilogue warps
+          fence_proxy_async();
+          asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
+          if (lane == 0 && q == 0 && cg < 2) {  // two issuing threads: warps 4 (block r0/64) and 8 (block r0/64 + 1)
+            const int blk = (r0 >> 6) + cg;
+            if (blk * 64 < limit) {
+              tma_store_4d(&p.tmC, sC + blk * kABytes, n0 + blk * 64, ow0, oh0, b);
+              tma_store_commit();
+            }
           }
         }
       }
-      if (p.tma_store && c64 < limit) {  // uniform over the 8 epilogue warps
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          tma_store_4d(&p.tmC, sA + (c64 >> 6) * kABytes, n0 + c64, ow0, oh0, b);
-          tma_store_commit();
-        }
-      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_read();
+    if (C_BLOCKS > 0 && p.tma_store && lane == 0 && q == 0 && cg < 2) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -313,15 +375,21 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------- host side
 
 template <int BLOCK_N, int STAGES>
-static int launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem);
+static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
+  constexpr int c_blocks = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + c_blocks * kABytes + 1024 + 256;
+  static int per_sm = 0;
+  if (!per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_gemm_kernel<BLOCK_N, STAGES>, kConvThreads, smem);
+    if (e != cudaSuccess || n < 1) return set_error(UC_EINVAL, "conv_gemm<%d,%d>: does not fit on an SM", BLOCK_N, STAGES);
+    constexpr int acc_cols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+    per_sm = std::min(n, 512 / (2 * acc_cols));  // TMEM: 512 columns per SM
   }
+  const int tiles = p.n_tiles * p.m_tiles;
+  const int grid = std::min(tiles, num_sms() * per_sm);
   conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d> launch: %s", BLOCK_N, STAGES, cudaGetErrorString(e));
@@ -329,10 +397,10 @@ static int launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t stream
 }
 
 static int pick_block_n(int Cout, int m_tiles, int gn_gs) {
-  // Measured on B200 (tools/bench_conv.py): the 128-wide tile with 3 stages (96 KB) wins or ties everywhere because
-  // two CTAs fit on an SM and one's epilogue overlaps the other's main loop; 96 plays the same role when GroupNorm
-  // groups (12/24/48/96 channels) must not straddle N tiles.  Larger tiles only when they are the only fit.
-  static const int cands[] = {128, 96, 64, 192, 256, 32, 16};
+  // Heuristic default for the persistent kernel (one CTA per SM for the wide tiles): fewest waves of the widest tile
+  // that does not waste more than a third of its columns.  unicorn_b200/engine.py autotunes block_n per layer on top
+  // of this (plan-time timing of the candidates), so this only has to be reasonable.
+  static const int cands[] = {256, 192, 128, 96, 64, 32, 16};
   const int sms = num_sms();
   int best = 0;
   double best_cost = -1.0;
@@ -340,12 +408,11 @@ static int pick_block_n(int Cout, int m_tiles, int gn_gs) {
     if (gn_gs > 0 && (bn % gn_gs) != 0) continue;  // GroupNorm groups must not straddle N tiles
     const int nt = (Cout + bn - 1) / bn;
     const long waste_cols = static_cast<long>(nt) * bn - Cout;
-    if (waste_cols * 8 > Cout && bn > 16 && gn_gs <= 0) continue;  // > 12.5 % padded columns
-    const long ctas = static_cast<long>(nt) * m_tiles;
-    const int per_sm = (bn <= 128) ? 2 : 1;  // resident CTAs per SM (shared memory)
-    const long waves = (ctas + static_cast<long>(sms) * per_sm - 1) / (static_cast<long>(sms) * per_sm);
-    // per-CTA time ~ (bn + 64) with the overlap of co-resident CTAs folded into per_sm
-    const double cost = static_cast<double>(waves) * (bn + 64);
+    if (waste_cols * 3 > static_cast<long>(nt) * bn && bn > 16 && gn_gs <= 0) continue;
+    const long tiles = static_cast<long>(nt) * m_tiles;
+    const int per_sm = bn <= 64 ? 2 : 1;
+    const long waves = (tiles + static_cast<long>(sms) * per_sm - 1) / (static_cast<long>(sms) * per_sm);
+    const double cost = static_cast<double>(waves) * (bn + 40) / per_sm;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -434,7 +501,7 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.kchunks = (d->Cin + kBlockK - 1) / kBlockK;
 
   const int gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 0;
-  const int bn = d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
+  const int bn = d->block_n == 129 ? 128 : d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
   if (bn == 0) return set_error(UC_EINVAL, "uc_conv2d: no N tile compatible with GroupNorm group size %d", gn_gs);
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(nt), static_cast<uint64_t>(d->Cout)};
@@ -462,16 +529,17 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 1 << 30;
   if (d->gn_stats && (bn % p.gn_gs) != 0)
     return set_error(UC_EINVAL, "uc_conv2d: N tile %d incompatible with GroupNorm group size %d", bn, p.gn_gs);
-  if (m_tiles > 65535) return set_error(UC_EINVAL, "uc_conv2d: too many M tiles (%d)", m_tiles);
-  dim3 grid((d->Cout + bn - 1) / bn, m_tiles, 1);
-  switch (bn) {
-    case 256: return launch_conv<256, 4>(p, grid, stream);
-    case 192: return launch_conv<192, 5>(p, grid, stream);
-    case 128: return launch_conv<128, 3>(p, grid, stream);
-    case 96: return launch_conv<96, 3>(p, grid, stream);
-    case 64: return launch_conv<64, 4>(p, grid, stream);
-    case 32: return launch_conv<32, 4>(p, grid, stream);
-    case 16: return launch_conv<16, 4>(p, grid, stream);
+  p.n_tiles = (d->Cout + bn - 1) / bn;
+  p.m_tiles = m_tiles;
+  switch (d->block_n == 129 ? 129 : bn) {
+    case 256: return launch_conv<256, 3>(p, stream);
+    case 192: return launch_conv<192, 4>(p, stream);
+    case 128: return launch_conv<128, 5>(p, stream);
+    case 129: return launch_conv<128, 2>(p, stream);  // two CTAs per SM (benchmarking aid)
+    case 96: return launch_conv<96, 3>(p, stream);
+    case 64: return launch_conv<64, 3>(p, stream);
+    case 32: return launch_conv<32, 4>(p, stream);
+    case 16: return launch_conv<16, 4>(p, stream);
     default: return set_error(UC_EINVAL, "uc_conv2d: unsupported block_n %d", bn);
   }
 }

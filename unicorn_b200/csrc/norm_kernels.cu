@@ -444,8 +444,8 @@ extern "C" int uc_groupnorm_apply(const void* x, int ldx, const void* stats, con
   if ((prior != nullptr) != (beta != nullptr)) return set_error(UC_EINVAL, "uc_groupnorm_apply: prior and beta go together");
   if (y2 && (!add2 || ldadd2 % 8 || ldy2 % 8)) return set_error(UC_EINVAL, "uc_groupnorm_apply: bad second output");
   const long total = HW * (C / 8);
-  // each block pays C scale/shift computations up front: give every block >= 16 elements per thread
-  const int gx = static_cast<int>(std::max<long>(1, std::min<long>((total + 256 * 16 - 1) / (256 * 16), static_cast<long>(num_sms()) * 4)));
+  // each block pays C scale/shift computations up front; keep ~2 elements (16 channels) per thread for parallelism
+  const int gx = static_cast<int>(std::max<long>(1, std::min<long>((total + 256 * 2 - 1) / (256 * 2), static_cast<long>(num_sms()) * 8)));
   if (C > 4096) return set_error(UC_EINVAL, "uc_groupnorm_apply: C too large");
   groupnorm_apply_kernel<<<dim3(gx, B), 256, 3 * C * sizeof(float), stream>>>(
       static_cast<const uint16_t*>(x), ldx, reinterpret_cast<const long long*>(stats), w, b, static_cast<uint16_t*>(y), ldy, HW, C, G,

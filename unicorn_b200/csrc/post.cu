@@ -150,7 +150,7 @@ __device__ __forceinline__ bool nms_hit(const float4 a, const float4 b, float th
 }
 
 __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restrict__ sorted, const int* __restrict__ count, float thr,
-                                                           float* __restrict__ out, int* __restrict__ out_count) {
+                                                           float* __restrict__ out, int* __restrict__ out_count, int max_keep) {
   extern __shared__ float4 kept_box[];                       // [kNmsKeepSmem]
   float* kept_cls = reinterpret_cast<float*>(kept_box + kNmsKeepSmem);  // [kNmsKeepSmem]
   __shared__ float4 cbox[kNmsChunk];
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restric
   __syncthreads();
   for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
     const int nk = nk_s;
+    if (nk >= max_keep) break;  // uniform: the first max_keep rows of the full result are already final
     const int ci = tid >> 2, sub = tid & 3;  // candidate within chunk, quarter of the kept list
     const int j = c0 + ci;
     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restric
     if (tid == 0) nk_s = nk + __popcll(kept_w[0]) + __popcll(kept_w[1]) + __popcll(kept_w[2]) + __popcll(kept_w[3]);
     __syncthreads();
   }
-  if (tid == 0) *out_count = nk_s;
+  if (tid == 0) *out_count = min(nk_s, max_keep);
 }
 
 }  // namespace uc
@@ -272,7 +273,7 @@ extern "C" long uc_postprocess_workspace_bytes(int max_anchors) {
   return A * 7 * 4 * 2 + a2 * 8 + 256;
 }
 
-extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, void* workspace,
+extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, int max_keep, void* workspace,
                               long workspace_bytes, float* out_dets, int* out_count, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!pred || !workspace || !out_dets || !out_count || A < 1 || ncls < 1) return set_error(UC_EINVAL, "uc_postprocess: bad arguments");
@@ -293,6 +294,6 @@ extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thr
     cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count);
+  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count, max_keep > 0 ? max_keep : 0x7fffffff);
   return check_launch("uc_postprocess");
 }

@@ -33,7 +33,7 @@ class _ConvGN:
 
 
 class UnicornEngine:
-    def __init__(self, state_dict, cfg_name, device="cuda"):
+    def __init__(self, state_dict, cfg_name, device="cuda", autotune=True):
         ops._lib.check(ops._lib.lib().uc_check_device(), "uc_check_device")  # fail loudly without an sm_100 GPU
         self.cfg_name = cfg_name
         self.cfg = CONFIGS[cfg_name]
@@ -45,6 +45,8 @@ class UnicornEngine:
         self._stats_arena = None
         self._stats_used = 0
         self._pos_cache = {}
+        self._bn_cache = {}
+        self.autotune = autotune
         self._load(state_dict)
 
     # ------------------------------------------------------------------------------------------ weights
@@ -125,6 +127,47 @@ class UnicornEngine:
             self._bufs[key] = t
         return t
 
+    # ------------------------------------------------------------------------------------------ conv autotuning
+    def conv(self, x, w, k, stride=1, pad=0, out=None, **kw):
+        """ops.conv2d with a plan-time choice of the N tile: the first time a layer shape is seen (outside CUDA-graph
+        capture) every valid block_n is timed on scratch outputs and the fastest is cached."""
+        B, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        gn = kw.get("gn_groups", 0)
+        key = (B, H, W, Cin, Cout, k, stride, pad, kw.get("act", 0), gn, kw.get("res") is not None, out.dtype)
+        bn = self._bn_cache.get(key)
+        if bn is None:
+            bn = 0
+            if self.autotune and not torch.cuda.is_current_stream_capturing():
+                bn = self._tune(x, w, k, stride, pad, out, kw, Cout, gn)
+            self._bn_cache[key] = bn
+        return ops.conv2d(x, w, k, k, stride, pad, out=out, block_n=bn, **kw)
+
+    def _tune(self, x, w, k, stride, pad, out, kw, Cout, gn):
+        gs = Cout // gn if gn else 0
+        cands = [0] + [b for b in (64, 96, 128, 192, 256) if (not gs or b % gs == 0) and b < 2 * Cout + 64]
+        scratch = torch.empty_like(out)
+        kw2 = dict(kw)
+        if gn:
+            kw2["gn_stats"] = torch.zeros(out.shape[0], gn, 2, dtype=torch.int64, device=self.dev)
+        best, best_t = 0, None
+        for bn in cands:
+            try:
+                for _ in range(2):
+                    ops.conv2d(x, w, k, k, stride, pad, out=scratch, block_n=bn, **kw2)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    ops.conv2d(x, w, k, k, stride, pad, out=scratch, block_n=bn, **kw2)
+                e1.record()
+                e1.synchronize()
+                t = e0.elapsed_time(e1)
+            except ops._lib.UnicornB200Error:
+                continue
+            if best_t is None or t < best_t * 0.97:  # require a 3 % win to leave the earlier (heuristic-first) choice
+                best, best_t = bn, t
+        return best
+
     def begin_frame(self):
         """Zero the GroupNorm statistics arena (one memset per frame; slots are handed out in call order)."""
         if self._stats_arena is None:
@@ -143,7 +186,7 @@ class UnicornEngine:
     def conv_gn(self, x, c, out, act=ACT_SILU, prior=None, beta=None, add2=None, out2=None):
         """x NHWC view -> out NHWC view (may be a channel slice)."""
         st = self._stats(c.groups)
-        ops.conv2d(x, c.w, c.k, c.k, c.stride, (c.k - 1) // 2, bias=c.bias, out=out, gn_stats=st, gn_groups=c.groups)
+        self.conv(x, c.w, c.k, c.stride, (c.k - 1) // 2, bias=c.bias, out=out, gn_stats=st, gn_groups=c.groups)
         ops.groupnorm_apply(out, st, c.gw, c.gb, c.groups, c.eps, act, prior=prior, beta=beta, add2=add2, out2=out2)
         return out
 
@@ -152,8 +195,8 @@ class UnicornEngine:
         B, H, W, C = x.shape
         t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape))
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
-        hid = ops.conv2d(t, bp["w1"], 1, 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
-        ops.conv2d(hid, bp["w2"], 1, 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
+        hid = self.conv(t, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
+        self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
         return x
 
     def csp(self, x, cp, out, tag):
@@ -189,7 +232,7 @@ class UnicornEngine:
                 lw, lb, cw, cb = P[f"down{i}"]
                 Bx, Hx, Wx, Cx = x.shape
                 t = ops.layernorm(x.view(-1, Cx), lw, lb, 1e-6, out=self.buf(f"{tag}.dn{i}", (Hx * Wx, Cx))).view(1, Hx, Wx, Cx)
-                x = ops.conv2d(t, cw, 2, 2, 2, 0, bias=cb, out=self.buf(f"{tag}.x{i}", (1, Hx // 2, Wx // 2, d[i])))
+                x = self.conv(t, cw, 2, 2, 0, bias=cb, out=self.buf(f"{tag}.x{i}", (1, Hx // 2, Wx // 2, d[i])))
             for j, bp in enumerate(P["stages"][i]):
                 self.convnext_block(x, bp, f"{tag}.s{i}")
             if i >= 1:
@@ -269,8 +312,8 @@ class UnicornEngine:
         """Unicorn.forward_upsample (unicorn.py:41-44,311-313): [1,h,w,256] -> embedding [1,2h,2w,128] fp16."""
         _, h, w, _ = feat.shape
         ps = ops.pixel_shuffle2(feat, out=self.buf(tag + ".ps", (1, 2 * h, 2 * w, 64)))
-        t = ops.conv2d(ps, self.P["up1"][0], 3, 3, 1, 1, bias=self.P["up1"][1], act=ACT_RELU, out=self.buf(tag + ".u1", (1, 2 * h, 2 * w, 256)))
-        return ops.conv2d(t, self.P["up3"][0], 3, 3, 1, 1, bias=self.P["up3"][1], out=self.buf(tag + ".emb", (1, 2 * h, 2 * w, 128), F16))
+        t = self.conv(ps, self.P["up1"][0], 3, 1, 1, bias=self.P["up1"][1], act=ACT_RELU, out=self.buf(tag + ".u1", (1, 2 * h, 2 * w, 256)))
+        return self.conv(t, self.P["up3"][0], 3, 1, 1, bias=self.P["up3"][1], out=self.buf(tag + ".emb", (1, 2 * h, 2 * w, 128), F16))
 
     # ------------------------------------------------------------------------------------------ correlation
     def propagate(self, embed_ref, embed_cur, values):

@@ -270,10 +270,11 @@ class PostWorkspace:
         self.max_anchors = max_anchors
 
 
-def postprocess_device(pred, ncls, conf, nms, ws):
-    """pred fp32 [A, 5+ncls] (decoded).  Launches only; ws.dets / ws.count hold the result."""
+def postprocess_device(pred, ncls, conf, nms, ws, max_keep=0):
+    """pred fp32 [A, 5+ncls] (decoded).  Launches only; ws.dets / ws.count hold the result.
+    max_keep > 0 returns exactly the first max_keep rows of the full NMS result."""
     A = pred.shape[0]
     assert pred.is_contiguous() and pred.dtype == torch.float32 and A <= ws.max_anchors
-    _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
+    _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), int(max_keep), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
                "uc_postprocess", 4)
     return ws.dets, ws.count

@@ -34,11 +34,14 @@ def preprocess(img_rgb, input_size):
 
 
 class UnicornSOTTrack:
-    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=3, use_graph=True):
+    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=3, use_graph=True, full_nms=False):
         self.eng, self.input_size = engine, tuple(input_size)
         self.confthre, self.nmsthre, self.max_inst = conf, nms, max_inst
         self.num_classes = 1
         self.use_graph = use_graph
+        # the driver consumes output[:max_inst] only (unicorn_sot.py:69-70): stop the greedy NMS scan there.
+        # full_nms=True reproduces the complete postprocess() list (used by the parity tests).
+        self.nms_keep = 0 if full_nms else max_inst
         H, W = self.input_size
         dev = engine.dev
         self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
@@ -60,7 +63,7 @@ class UnicornSOTTrack:
         e_pre, e_cur = e.upsample(f_pre, "embp"), e.upsample(f_cur, "embc")
         priors = e.propagate(e_pre, e_cur, self.lbs_pre)
         out = e.head(fpn, priors, "sot")
-        ops.postprocess_device(out[0], 1, self.confthre, self.nmsthre, self.ws)
+        ops.postprocess_device(out[0], 1, self.confthre, self.nmsthre, self.ws, max_keep=self.nms_keep)
         self.last = dict(fpn=fpn, feat=seq["feat"], inter_pre=f_pre, inter_cur=f_cur, embed_pre=e_pre, embed_cur=e_cur, priors=priors, head=out)
 
     def initialize_tensor(self, ref_frame, init_box_xyxy):
