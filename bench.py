@@ -169,12 +169,10 @@ def main():
     host_frames = [frames[1 + i:2 + i].contiguous().pin_memory() for i in range(n_frames - 1)]
     dev_frames = [f.to(dev) for f in host_frames]
     # warm-up (builds the CUDA graph on the first call)
-    _lib.LAUNCHES = 0
     trk.track_tensor(host_frames[0])
-    launches_first = _lib.LAUNCHES  # eager warm-up + capture = 2 passes
     for i in range(Wm):
         trk.track_tensor(host_frames[i % len(host_frames)])
-    launches_per_frame = launches_first // 2
+    launches_per_frame = trk.launches_per_frame  # counted while the frame was captured into the CUDA graph
 
     def sync_all():
         torch.cuda.synchronize()

@@ -254,3 +254,25 @@ def test_postprocess_max_keep_is_a_prefix():
         part, c2 = ops.postprocess_device(pred, 1, 0.2, 0.65, ws2, max_keep=k)
         assert int(c2.item()) == min(k, n_full)
         assert torch.equal(part[:min(k, n_full)], full[:min(k, n_full)])
+
+
+def test_msda_dropin_module_signature():
+    """The reference's autograd wrapper calls MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, attn, im2col_step)
+    (ops/functions/ms_deform_attn_func.py:22-28)."""
+    from unicorn_b200 import compat
+    compat.install()
+    import MultiScaleDeformableAttention as MSDA
+    g = G(12)
+    hw = [(9, 7), (5, 4)]
+    S = sum(h * w for h, w in hw)
+    value = torch.randn(2, S, 4, 16, generator=g).to(dev)
+    loc = torch.rand(2, 11, 4, 2, 3, 2, generator=g).to(dev)
+    attn = torch.softmax(torch.randn(2, 11, 4, 6, generator=g), -1).view(2, 11, 4, 2, 3).to(dev)
+    shapes = torch.as_tensor(hw, dtype=torch.long, device=dev)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    out = MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 64)
+    close(out, _msda_ref(value, hw, loc, attn), 1e-5, "msda drop-in")
+    with pytest.raises(RuntimeError):
+        MSDA.ms_deform_attn_forward(value.cpu(), shapes, lsi, loc, attn, 64)
+    with pytest.raises(NotImplementedError):
+        MSDA.ms_deform_attn_backward()

@@ -94,8 +94,11 @@ class UnicornSOTTrack:
             self._frame()  # warm-up: allocates every buffer, sets kernel attributes
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            from . import _lib
+            l0 = _lib.LAUNCHES
             with torch.cuda.graph(g):
                 self._frame()
+            self.launches_per_frame = _lib.LAUNCHES - l0  # kernels recorded in the graph (C-ABI launches only)
             self.graph = g
             self.graph.replay()
         else:
