@@ -21,3 +21,6 @@ for i in range(nfr):
     l0 = _lib.LAUNCHES
     trk.track_tensor(frames[1 + i:2 + i])
     print("frame", i, "launches", _lib.LAUNCHES - l0)
+if len(sys.argv) > 3:
+    eng.save_tuning(sys.argv[3])
+    print("saved tuning table", sys.argv[3], len(eng._bn_cache))

@@ -410,9 +410,8 @@ static int pick_block_n(int Cout, int m_tiles, int gn_gs) {
     const long waste_cols = static_cast<long>(nt) * bn - Cout;
     if (waste_cols * 3 > static_cast<long>(nt) * bn && bn > 16 && gn_gs <= 0) continue;
     const long tiles = static_cast<long>(nt) * m_tiles;
-    const int per_sm = bn <= 64 ? 2 : 1;
-    const long waves = (tiles + static_cast<long>(sms) * per_sm - 1) / (static_cast<long>(sms) * per_sm);
-    const double cost = static_cast<double>(waves) * (bn + 40) / per_sm;
+    const long waves = (tiles + sms - 1) / sms;  // one persistent CTA per SM
+    const double cost = static_cast<double>(waves) * (bn + 40);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;

@@ -14,6 +14,8 @@ All buffers are allocated on first use per input resolution and then reused, so 
 allocation and can be captured in a CUDA graph (see unicorn_b200/sot.py).  torch is used only as the device-memory
 allocator and stream/graph plumbing; every arithmetic step is a launch through the C ABI (unicorn_b200/ops.py).
 """
+import os
+
 import torch
 
 from . import ops
@@ -45,8 +47,11 @@ class UnicornEngine:
         self._stats_arena = None
         self._stats_used = 0
         self._pos_cache = {}
+        self._side_streams = None
         self._bn_cache = {}
+        self._bn_dirty = False
         self.autotune = autotune
+        self.load_tuning()
         self._load(state_dict)
 
     # ------------------------------------------------------------------------------------------ weights
@@ -135,11 +140,13 @@ class UnicornEngine:
         Cout = w.shape[0]
         gn = kw.get("gn_groups", 0)
         key = (B, H, W, Cin, Cout, k, stride, pad, kw.get("act", 0), gn, kw.get("res") is not None, out.dtype)
+        key = "|".join(str(v) for v in key)
         bn = self._bn_cache.get(key)
         if bn is None:
             bn = 0
             if self.autotune and not torch.cuda.is_current_stream_capturing():
                 bn = self._tune(x, w, k, stride, pad, out, kw, Cout, gn)
+                self._bn_dirty = True
             self._bn_cache[key] = bn
         return ops.conv2d(x, w, k, k, stride, pad, out=out, block_n=bn, **kw)
 
@@ -150,7 +157,7 @@ class UnicornEngine:
         kw2 = dict(kw)
         if gn:
             kw2["gn_stats"] = torch.zeros(out.shape[0], gn, 2, dtype=torch.int64, device=self.dev)
-        best, best_t = 0, None
+        best, best_t, times = 0, None, []
         for bn in cands:
             try:
                 for _ in range(2):
@@ -164,9 +171,30 @@ class UnicornEngine:
                 t = e0.elapsed_time(e1)
             except ops._lib.UnicornB200Error:
                 continue
+            times.append((bn, round(t * 250, 1)))  # us per launch
             if best_t is None or t < best_t * 0.97:  # require a 3 % win to leave the earlier (heuristic-first) choice
                 best, best_t = bn, t
+        if os.environ.get("UC_TUNE_LOG"):
+            print("tune", tuple(x.shape), "->", Cout, "k", k, "s", stride, "gn", gn, "best", best, times, flush=True)
         return best
+
+    def tuning_path(self):
+        return os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned", f"{self.cfg_name}.json")
+
+    def load_tuning(self, path=None):
+        """Per-layer N-tile choices measured on a B200 and committed under unicorn_b200/tuned/ (plan-time autotuning
+        fills in whatever is missing).  Returns the number of entries loaded."""
+        import json
+        path = path or self.tuning_path()
+        if os.path.exists(path):
+            self._bn_cache.update(json.load(open(path)))
+            return len(self._bn_cache)
+        return 0
+
+    def save_tuning(self, path):
+        import json
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        json.dump(self._bn_cache, open(path, "w"), indent=0, sort_keys=True)
 
     def begin_frame(self):
         """Zero the GroupNorm statistics arena (one memset per frame; slots are handed out in call order)."""
@@ -332,9 +360,26 @@ class UnicornEngine:
         fpn: 3 NHWC bf16 maps; priors: 3 fp32 [1,h,w] maps or None (MOT: zero prior == no fusion term).
         Returns fp32 [1, A, 5+ncls_mode]."""
         sfx = "_sot" if mode == "sot" else ""
-        ro_outs, cls_outs, hw = [], [], []
+        ro_outs, cls_outs, hw = [None] * 3, [None] * 3, [None] * 3
         ncls = 1 if mode == "sot" else self.ncls
-        for k in range(3):
+        # The three pyramid levels are independent chains of ~30 small kernels (level 2 has 1000 pixels = 8 M tiles):
+        # run them on three streams (fork/join is captured into the CUDA graph) so they fill the SMs together.
+        main = torch.cuda.current_stream()
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+        for s_ in self._side_streams:  # fork before anything of the head is enqueued on the main stream
+            s_.wait_stream(main)
+        for k in (1, 2):
+            with torch.cuda.stream(self._side_streams[k - 1]):
+                self._head_level(k, fpn, priors, sfx, ro_outs, cls_outs, hw)
+        self._head_level(0, fpn, priors, sfx, ro_outs, cls_outs, hw)
+        for s_ in self._side_streams:  # join
+            main.wait_stream(s_)
+        A = sum(h * w for h, w in hw)
+        return ops.head_decode(ro_outs, cls_outs, hw, STRIDES, ncls, out=self.buf(f"head.out{ncls}", (1, A, 5 + ncls), F32))
+
+    def _head_level(self, k, fpn, priors, sfx, ro_outs, cls_outs, hw):
+        if True:
             L = self.P["head"][k]
             _, h, w, _ = fpn[k].shape
             x = self.buf(f"head{k}.x", (1, h, w, 256))
@@ -349,11 +394,9 @@ class UnicornEngine:
                     cur = self.conv_gn(cur, c, self.buf(f"head{k}.{name}{i % 2}", (1, h, w, 256)))
                 feats.append(cur)
             row, rob, cw, cb, _ = L["pred" + sfx]
-            cls_outs.append(ops.conv2d(feats[0], cw, 1, 1, bias=cb, out=self.buf(f"head{k}.clso", (1, h, w, 8), F32)))
-            ro_outs.append(ops.conv2d(feats[1], row, 1, 1, bias=rob, out=self.buf(f"head{k}.roo", (1, h, w, 8), F32)))
-            hw.append((h, w))
-        A = sum(h * w for h, w in hw)
-        return ops.head_decode(ro_outs, cls_outs, hw, STRIDES, ncls, out=self.buf(f"head.out{ncls}", (1, A, 5 + ncls), F32))
+            cls_outs[k] = ops.conv2d(feats[0], cw, 1, 1, bias=cb, out=self.buf(f"head{k}.clso", (1, h, w, 8), F32))
+            ro_outs[k] = ops.conv2d(feats[1], row, 1, 1, bias=rob, out=self.buf(f"head{k}.roo", (1, h, w, 8), F32))
+            hw[k] = (h, w)
 
 
 def _rows(t):
