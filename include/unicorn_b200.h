@@ -158,6 +158,19 @@ UC_API long uc_postprocess_workspace_bytes(int max_anchors);
 UC_API int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, int max_keep, void* workspace,
                           long workspace_bytes, float* out_dets, int* out_count, void* stream);
 
+/* Instance-embedding sampling at box centres (unicorn/evaluators/mot_evaluator.py:1024-1034): embed NHWC 16-bit
+ * [h,w,C] (pixel stride ld), boxes f32 [n,ldb] xyxy in network-input pixels, stride = 8; grid_sample(bilinear,
+ * border, align_corners=False) semantics incl. the reference's clamp/normalise step.  n = min(*count_dev, n_max)
+ * (count_dev may be NULL).  out f32 [n_max, C]. */
+UC_API int uc_sample_embed(const void* embed, int ld, int h, int w, int C, int dtype, const float* boxes, int ldb,
+                           const int* count_dev, int n_max, float stride, float* out, void* stream);
+/* Quasi-dense association score (unicorn/tracker/quasi_dense_embed_tracker.py:166-175): scores = (softmax_rows(F) +
+ * softmax_cols(F)) / 2 with F = E M^T, zeroed where labels differ (labels may be NULL).  workspace >= N*M+2N+2M floats. */
+UC_API int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, int N, int M, int C, const float* det_labels,
+                        const float* memo_labels, float* workspace, float* scores, void* stream);
+/* torchvision.ops.box_iou: out[i,j] = IoU(a_i, b_j), boxes xyxy f32 with row strides. */
+UC_API int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,86 @@
+"""MOT association on the GPU path against the oracle (and through it the reference): embedding sampling, the
+quasi-dense tracker's ids over a 25-frame sequence (bit-matching track assignments), and the MOT driver."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def test_sample_embed_matches_grid_sample():
+    import tracker_oracle as to
+    from unicorn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(1, 128, 20, 36, generator=g)
+    boxes = torch.rand(40, 4, generator=g) * torch.tensor([288.0, 160.0, 288.0, 160.0])
+    boxes[:, 2:] += boxes[:, :2]
+    boxes[0] = torch.tensor([-50.0, -20.0, 4.0, 6.0])       # centre clamps to the border
+    boxes[1] = torch.tensor([280.0, 150.0, 400.0, 300.0])
+    ref = to.sample_embeddings(emb, boxes, (160, 288))
+    e16 = emb[0].permute(1, 2, 0).contiguous().half().cuda().unsqueeze(0)
+    cnt = torch.tensor([37], dtype=torch.int32, device="cuda")
+    got = ops.sample_embed(e16, boxes.cuda().contiguous(), 40, 8.0, count=cnt).cpu()
+    ref16 = to.sample_embeddings(emb.half().float(), boxes, (160, 288))
+    assert torch.allclose(got[:37], ref16[:37], atol=2e-3), (got[:37] - ref16[:37]).abs().max()
+    assert (got[37:] == 0).all()
+    assert (got[:37] - ref[:37]).abs().max() < 2e-2
+
+
+def test_bisoftmax_and_iou_kernels():
+    import tracker_oracle as to
+    from unicorn_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    E, M = torch.randn(23, 128, generator=g), torch.randn(57, 128, generator=g)
+    le, lm = torch.randint(0, 3, (23,), generator=g).float(), torch.randint(0, 3, (57,), generator=g).float()
+    f = E @ M.t()
+    ref = (f.softmax(1) + f.softmax(0)) / 2 * (le[:, None] == lm[None, :]).float()
+    got = ops.bisoftmax(E.cuda(), M.cuda(), le.cuda(), lm.cuda()).cpu()
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-4)
+    a = torch.rand(31, 4, generator=g) * 100
+    a[:, 2:] += a[:, :2]
+    b = torch.rand(17, 4, generator=g) * 100
+    b[:, 2:] += b[:, :2]
+    assert torch.allclose(ops.box_iou(a.cuda(), b.cuda()).cpu(), to.box_iou(a, b), atol=1e-6)
+
+
+def test_qd_tracker_ids_match_reference():
+    from unicorn_b200.synthetic import make_detections
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    g = np.load(os.path.join(ROOT, "tests", "golden", "qd_tracker.npz"))
+    frames = make_detections(int(g["n_frames"]), int(g["n_obj"]), int(g["seed"]))
+    trk = QuasiDenseEmbedTracker()
+    for i, (boxes, feats) in enumerate(frames):
+        b, _, ids = trk.match(boxes, torch.ones(boxes.size(0)), feats, i + 1)
+        assert np.array_equal(ids.numpy(), g[f"ids_{i}"]), (i, ids, g[f"ids_{i}"])
+        assert np.allclose(b.numpy(), g[f"boxes_{i}"])
+    assert trk.num_tracklets == int(g["num_tracklets"])
+
+
+def test_mot_driver_runs_and_is_consistent():
+    """tiny model, 4 frames, 3 moving objects: whole mode + interaction + sampling + association end to end; the
+    sampled embeddings are checked against the oracle's grid_sample on the engine's own embedding map."""
+    import tracker_oracle as to
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.mot import UnicornMOTTracker
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.weights import make_state_dict
+    name = "unicorn_track_tiny"
+    eng = UnicornEngine(make_state_dict(name, 0), name)
+    frames, _ = make_video(4, 320, 320, seed=1, n_obj=3)
+    mot = UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7)
+    all_ids = []
+    for t in range(4):
+        boxes, ids = mot.step_tensor(frames[t:t + 1])
+        all_ids.append(ids)
+        d, f = mot.last["dets"], mot.last["feats"]
+        assert d.shape[0] > 0
+        emb = mot.last["embed"].float().permute(0, 3, 1, 2).cpu()
+        ref = to.sample_embeddings(emb, d[:, :4], (320, 320))
+        assert torch.allclose(f, ref, atol=2e-3), (f - ref).abs().max()
+        assert (ids >= 0).all() and ids.numel() == ids.unique().numel()
+    assert mot.tracker.num_tracklets >= 1

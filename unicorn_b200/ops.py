@@ -278,3 +278,31 @@ def postprocess_device(pred, ncls, conf, nms, ws, max_keep=0):
     _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), int(max_keep), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
                "uc_postprocess", 4)
     return ws.dets, ws.count
+
+
+def sample_embed(embed, boxes, n_max, stride=8.0, count=None, out=None):
+    """embed NHWC 16-bit [1,h,w,C]; boxes fp32 [>=n_max, >=4] (device); returns fp32 [n_max, C]."""
+    _, h, w, C = embed.shape
+    if out is None:
+        out = torch.zeros(n_max, C, dtype=torch.float32, device=embed.device)
+    _lib.check(_L().uc_sample_embed(_p(embed), _nhwc_ld(embed), h, w, C, _DT[embed.dtype], _p(boxes), boxes.stride(0), _p(count), n_max,
+                                    _f(stride), _p(out), _S()), "uc_sample_embed")
+    return out
+
+
+def bisoftmax(det_embeds, memo_embeds, det_labels=None, memo_labels=None):
+    N, C = det_embeds.shape
+    M = memo_embeds.shape[0]
+    ws = torch.empty(N * M + 2 * N + 2 * M, dtype=torch.float32, device=det_embeds.device)
+    scores = torch.empty(N, M, dtype=torch.float32, device=det_embeds.device)
+    _lib.check(_L().uc_bisoftmax(_p(det_embeds), _p(memo_embeds), N, M, C, _p(det_labels), _p(memo_labels), _p(ws), _p(scores), _S()),
+               "uc_bisoftmax", 3)
+    return scores
+
+
+def box_iou(a, b):
+    N, M = a.shape[0], b.shape[0]
+    out = torch.empty(N, M, dtype=torch.float32, device=a.device)
+    if N and M:
+        _lib.check(_L().uc_box_iou(_p(a), a.stride(0), N, _p(b), b.stride(0), M, _p(out), _S()), "uc_box_iou")
+    return out

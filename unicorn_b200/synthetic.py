@@ -33,3 +33,29 @@ def make_video(n_frames, H, W, seed=0, n_obj=1):
             boxes[t, o] = torch.tensor([x, y, x + bw, y + bh], dtype=torch.float32)
         frames[t] = f.clamp_(0, 255)
     return frames, boxes
+
+
+def make_detections(n_frames=25, n_obj=14, seed=0, dim=128, W=1280.0, H=800.0):
+    """Seeded synthetic per-frame detections for association tests: objects move linearly, each carries a noisy copy
+    of its identity embedding; scores vary so that the tracker's thresholds (0.5 / 0.8) are exercised; a few
+    duplicates and low-score clutter boxes are added.  Returns [(boxes [N,5] x1y1x2y2s, feats [N,dim]), ...]."""
+    g = torch.Generator(device="cpu").manual_seed(4000 + seed)
+    ident = torch.randn(n_obj, dim, generator=g) * 1.5
+    pos = torch.rand(n_obj, 2, generator=g) * torch.tensor([W * 0.7, H * 0.7])
+    vel = (torch.rand(n_obj, 2, generator=g) - 0.5) * 16
+    size = torch.rand(n_obj, 2, generator=g) * 80 + 40
+    out = []
+    for t in range(n_frames):
+        present = torch.rand(n_obj, generator=g) > 0.12
+        p = pos + vel * t + torch.randn(n_obj, 2, generator=g) * 1.5
+        boxes = torch.cat([p, p + size], 1)
+        scores = (0.45 + 0.55 * torch.rand(n_obj, generator=g)).clamp(max=0.99)
+        feats = ident + 0.25 * torch.randn(n_obj, dim, generator=g)
+        b, s, f = boxes[present], scores[present], feats[present]
+        # duplicate of the first present box (slightly shifted, lower score) and two clutter boxes
+        if b.size(0) > 0:
+            b = torch.cat([b, b[:1] + 3.0, torch.rand(2, 2, generator=g).repeat(1, 2) * 400 + torch.tensor([0, 0, 60.0, 60.0])])
+            s = torch.cat([s, s[:1] * 0.9, torch.tensor([0.2, 0.35])])
+            f = torch.cat([f, f[:1] + 0.1 * torch.randn(1, dim, generator=g), torch.randn(2, dim, generator=g)])
+        out.append((torch.cat([b, s[:, None]], 1).float(), f.float()))
+    return out
