@@ -72,7 +72,10 @@ def test_mot_driver_runs_and_is_consistent():
     name = "unicorn_track_tiny"
     eng = UnicornEngine(make_state_dict(name, 0), name)
     frames, _ = make_video(4, 320, 320, seed=1, n_obj=3)
-    mot = UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7)
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    # seeded random weights give low scores: lower the tracker's score gates so that tracklets are created
+    mot = UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7, score_thr=0.02,
+                            tracker=QuasiDenseEmbedTracker(init_score_thr=0.05, obj_score_thr=0.03))
     all_ids = []
     for t in range(4):
         boxes, ids = mot.step_tensor(frames[t:t + 1])
