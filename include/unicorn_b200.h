@@ -168,8 +168,10 @@ UC_API int uc_sample_embed(const void* embed, int ld, int h, int w, int C, int d
  * softmax_cols(F)) / 2 with F = E M^T, zeroed where labels differ (labels may be NULL).  workspace >= N*M+2N+2M floats. */
 UC_API int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, int N, int M, int C, const float* det_labels,
                         const float* memo_labels, float* workspace, float* scores, void* stream);
-/* torchvision.ops.box_iou: out[i,j] = IoU(a_i, b_j), boxes xyxy f32 with row strides. */
-UC_API int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, void* stream);
+/* Pairwise IoU out[i,j] of xyxy f32 boxes with row strides.  plus_one = 0: torchvision.ops.box_iou
+ * (quasi_dense_embed_tracker.py:80,146); plus_one = 1: cython_bbox.bbox_overlaps' inclusive-pixel convention
+ * (unicorn/tracker/matching.py:65-68, ByteTrack). */
+UC_API int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, int plus_one, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,26 @@ def test_mot_driver_runs_and_is_consistent():
         assert torch.allclose(f, ref, atol=2e-3), (f - ref).abs().max()
         assert (ids >= 0).all() and ids.numel() == ids.unique().numel()
     assert mot.tracker.num_tracklets >= 1
+
+
+def test_byte_tracker_matches_reference_logic():
+    """30 frames of seeded detections through BYTETracker.update vs the reference's own update() flow
+    (tests/golden/byte_tracker.npz: reference STrack/Kalman/association code with lap/cython_bbox emulated)."""
+    import types
+    from unicorn_b200.synthetic import make_detections
+    from unicorn_b200.tracker import BYTETracker
+    from unicorn_b200.tracker.byte_tracker import STrack
+    g = np.load(os.path.join(ROOT, "tests", "golden", "byte_tracker.npz"))
+    args = types.SimpleNamespace(track_thresh=0.6, track_buffer=30, match_thresh=0.9, mot20=False)
+    STrack._count = 0
+    trk = BYTETracker(args)
+    frames = make_detections(int(g["n_frames"]), int(g["n_obj"]), int(g["seed"]))
+    for i, (boxes, _) in enumerate(frames):
+        out = trk.update(boxes.numpy().copy(), (800, 1280), (800, 1280))
+        rows = np.array([[t.track_id, *t.tlwh, t.score] for t in out]).reshape(-1, 6)
+        rows = rows[np.argsort(rows[:, 0])] if len(rows) else rows
+        ref = g[f"f{i}"]
+        assert rows.shape == ref.shape, (i, rows[:, 0], ref[:, 0])
+        assert np.array_equal(rows[:, 0], ref[:, 0]), (i, rows[:, 0], ref[:, 0])   # bit-matching track ids
+        assert np.allclose(rows[:, 1:], ref[:, 1:], rtol=1e-4, atol=1e-2), (i, np.abs(rows - ref).max())
+    assert STrack._count == int(g["total_ids"])

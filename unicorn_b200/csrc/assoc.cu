@@ -82,14 +82,16 @@ __global__ void __launch_bounds__(256) bisoftmax_kernel(const float* __restrict_
   scores[t] = s;
 }
 
+// plus1 = 0: torchvision.ops.box_iou; plus1 = 1: cython_bbox.bbox_overlaps (inclusive-pixel convention used by ByteTrack,
+// unicorn/tracker/matching.py:65-68)
 __global__ void __launch_bounds__(256) box_iou_kernel(const float* __restrict__ a, int lda, int N, const float* __restrict__ b, int ldb,
-                                                       int M, float* __restrict__ out) {
+                                                       int M, float* __restrict__ out, float plus1) {
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long>(N) * M) return;
   const float* p = a + (t / M) * lda;
   const float* q = b + (t % M) * ldb;
-  const float area1 = (p[2] - p[0]) * (p[3] - p[1]), area2 = (q[2] - q[0]) * (q[3] - q[1]);
-  const float w = fmaxf(fminf(p[2], q[2]) - fmaxf(p[0], q[0]), 0.f), h = fmaxf(fminf(p[3], q[3]) - fmaxf(p[1], q[1]), 0.f);
+  const float area1 = (p[2] - p[0] + plus1) * (p[3] - p[1] + plus1), area2 = (q[2] - q[0] + plus1) * (q[3] - q[1] + plus1);
+  const float w = fmaxf(fminf(p[2], q[2]) - fmaxf(p[0], q[0]) + plus1, 0.f), h = fmaxf(fminf(p[3], q[3]) - fmaxf(p[1], q[1]) + plus1, 0.f);
   const float inter = w * h;
   out[t] = inter / (area1 + area2 - inter);
 }
@@ -123,8 +125,8 @@ extern "C" int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, i
   return check_launch("uc_bisoftmax");
 }
 
-extern "C" int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, void* stream_v) {
+extern "C" int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, int plus_one, void* stream_v) {
   if (!a || !b || !out || N < 1 || M < 1 || lda < 4 || ldb < 4) return set_error(UC_EINVAL, "uc_box_iou: bad arguments");
-  box_iou_kernel<<<static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(a, lda, N, b, ldb, M, out);
+  box_iou_kernel<<<static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(a, lda, N, b, ldb, M, out, plus_one ? 1.f : 0.f);
   return check_launch("uc_box_iou");
 }

@@ -300,9 +300,9 @@ def bisoftmax(det_embeds, memo_embeds, det_labels=None, memo_labels=None):
     return scores
 
 
-def box_iou(a, b):
+def box_iou(a, b, plus_one=False):
     N, M = a.shape[0], b.shape[0]
     out = torch.empty(N, M, dtype=torch.float32, device=a.device)
     if N and M:
-        _lib.check(_L().uc_box_iou(_p(a), a.stride(0), N, _p(b), b.stride(0), M, _p(out), _S()), "uc_box_iou")
+        _lib.check(_L().uc_box_iou(_p(a), a.stride(0), N, _p(b), b.stride(0), M, _p(out), int(plus_one), _S()), "uc_box_iou")
     return out
