@@ -88,8 +88,10 @@ typedef struct UcConv2d {
 UC_API int uc_conv2d(const UcConv2d* d, void* stream);
 
 /* ConvNeXt stem: Conv2d(3,C0,k4,s4)+bias then channels_first LayerNorm (backbone/convnext.py:77-80,179-184).
- * img fp32 NCHW [B,3,H,W]; w48 fp32 [48][C0] with k=(ci*4+kh)*4+kw; out NHWC bf16 [B,H/4,W/4,C0]. */
-UC_API int uc_stem_ln(const float* img, const float* w48, const float* bias, const float* lnw, const float* lnb,
+ * img: fp32 NCHW [B,3,H,W] (PreprocessorX output, unicorn_sot.py:114-123) or, with img_is_u8_hwc = 1, the uint8 HWC
+ * BGR frame [B,H,W,3] as cv2 delivers it (the permute / float conversion is fused into the load);
+ * w48 fp32 [48][C0] with k=(ci*4+kh)*4+kw; out NHWC bf16 [B,H/4,W/4,C0]. */
+UC_API int uc_stem_ln(const void* img, int img_is_u8_hwc, const float* w48, const float* bias, const float* lnw, const float* lnb,
                       void* out_bf16, int B, int H, int W, int C0, float eps, void* stream);
 
 /* ConvNeXt block front half: depthwise 7x7 (pad 3)+bias then LayerNorm over C (convnext.py:43-45).

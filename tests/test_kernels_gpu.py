@@ -276,3 +276,16 @@ def test_msda_dropin_module_signature():
         MSDA.ms_deform_attn_forward(value.cpu(), shapes, lsi, loc, attn, 64)
     with pytest.raises(NotImplementedError):
         MSDA.ms_deform_attn_backward()
+
+
+def test_stem_uint8_hwc_equals_float_nchw():
+    from unicorn_b200 import ops
+    g = G(13)
+    C0, H, W = 96, 64, 96
+    u8 = (torch.rand(1, H, W, 3, generator=g) * 255).to(torch.uint8).to(dev)
+    f32 = u8.float().permute(0, 3, 1, 2).contiguous()
+    w = (torch.randn(C0, 3, 4, 4, generator=g) / 7).to(dev)
+    b, lw, lb = (torch.randn(C0, generator=g).to(dev) for _ in range(3))
+    a = ops.stem_ln(u8, ops.pack_stem_weight(w), b, lw, lb)
+    c = ops.stem_ln(f32, ops.pack_stem_weight(w), b, lw, lb)
+    assert torch.equal(a, c)

@@ -10,7 +10,7 @@ namespace uc {
 // img fp32 NCHW [B,3,H,W]; w packed [48][C0] fp32 (k = (ci*4+kh)*4+kw); out NHWC bf16 [B,H/4,W/4,C0].
 // One warp handles 4 horizontally adjacent output pixels; lane owns channels lane+32*i.
 template <int CPL>  // channels per lane = C0/32
-__global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ img, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ img, const uint8_t* __restrict__ img_u8, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ lnw,
                                                        const float* __restrict__ lnb, uint16_t* __restrict__ out, int B,
                                                        int H, int W, float eps) {
@@ -35,13 +35,17 @@ __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ 
       const int ow = ow0 + p;
       {
         const int k = lane, ci = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
-        in0[p] = (ow < Wo) ? __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw) : 0.f;
+        if (ow >= Wo) in0[p] = 0.f;
+        else if (img_u8) in0[p] = static_cast<float>(__ldg(img_u8 + ((static_cast<long>(b) * H + oh * 4 + kh) * W + ow * 4 + kw) * 3 + ci));
+        else in0[p] = __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw);
       }
       {
         const int k = lane + 32;
         if (k < 48) {
           const int ci = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
-          in1[p] = (ow < Wo) ? __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw) : 0.f;
+          if (ow >= Wo) in1[p] = 0.f;
+          else if (img_u8) in1[p] = static_cast<float>(__ldg(img_u8 + ((static_cast<long>(b) * H + oh * 4 + kh) * W + ow * 4 + kw) * 3 + ci));
+          else in1[p] = __ldg(img + ((static_cast<long>(b) * 3 + ci) * H + oh * 4 + kh) * W + ow * 4 + kw);
         } else {
           in1[p] = 0.f;
         }
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
 
 using namespace uc;
 
-extern "C" int uc_stem_ln(const float* img, const float* w48, const float* bias, const float* lnw, const float* lnb,
+extern "C" int uc_stem_ln(const void* img, int img_is_u8_hwc, const float* w48, const float* bias, const float* lnw, const float* lnb,
                           void* out_bf16, int B, int H, int W, int C0, float eps, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!img || !w48 || !bias || !lnw || !lnb || !out_bf16) return set_error(UC_EINVAL, "uc_stem_ln: null pointer");
@@ -370,7 +374,8 @@ extern "C" int uc_stem_ln(const float* img, const float* w48, const float* bias,
 #define UC_STEM(CPL)                                                                                                   \
   case CPL: {                                                                                                          \
     cudaFuncSetAttribute(stem_ln_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);                 \
-    stem_ln_kernel<CPL><<<grid, 256, smem, stream>>>(img, w48, bias, lnw, lnb, out, B, H, W, eps);                     \
+    stem_ln_kernel<CPL><<<grid, 256, smem, stream>>>(img_is_u8_hwc ? nullptr : static_cast<const float*>(img),                  \
+                                                     img_is_u8_hwc ? static_cast<const uint8_t*>(img) : nullptr, w48, bias, lnw, lnb, out, B, H, W, eps);                     \
   } break;
   switch (C0 / 32) {
     UC_STEM(1) UC_STEM(2) UC_STEM(3) UC_STEM(4) UC_STEM(6) UC_STEM(8)

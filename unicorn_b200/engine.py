@@ -48,6 +48,7 @@ class UnicornEngine:
         self._stats_used = 0
         self._pos_cache = {}
         self._side_streams = None
+        self._fork_stream = None
         self._bn_cache = {}
         self._bn_dirty = False
         self.autotune = autotune
@@ -241,11 +242,30 @@ class UnicornEngine:
         return self.conv_gn(cat, cp["c3"], out)
 
     # ------------------------------------------------------------------------------------------ backbone + neck
-    def backbone(self, img, tag="cur"):
+    def backbone(self, img, tag="cur", side=None):
+        """features + neck.  `side(seq_dict)` (optional) is run on a second stream concurrently with the neck: in the SOT
+        frame the interaction -> upsample -> correlation chain only needs the stride-16 backbone feature."""
+        feats, seq = self.features(img, tag)
+        if side is None:
+            return self.neck(feats, tag), seq
+        main = torch.cuda.current_stream()
+        if self._fork_stream is None:
+            self._fork_stream = torch.cuda.Stream(device=self.dev)
+        self._fork_stream.wait_stream(main)
+        with torch.cuda.stream(self._fork_stream):
+            side_out = side(seq)
+        fpn = self.neck(feats, tag)
+        main.wait_stream(self._fork_stream)
+        return fpn, seq, side_out
+
+    def features(self, img, tag="cur"):
         """img fp32 NCHW [1,3,H,W] -> (fpn_outs (p3,p4,p5) NHWC bf16, seq_dict{feat NHWC view, h, w}).
         ConvNeXt.forward_features (convnext.py:141-154) + YOLOPAFPNNEW.forward (yolo_pafpn_new.py:137-155)."""
         P, d = self.P, self.dims
-        B, _, H, W = img.shape
+        if img.dtype == torch.uint8:  # HWC BGR frame straight from the decoder / cv2.resize
+            B, H, W, _ = img.shape
+        else:
+            B, _, H, W = img.shape
         assert B == 1 and H % 32 == 0 and W % 32 == 0
         h8, w8, h16, w16, h32, w32 = H // 8, W // 8, H // 16, W // 16, H // 32, W // 32
         # concat buffers of the neck (producers write into slices)
@@ -269,7 +289,18 @@ class UnicornEngine:
                 dst = {1: cat_p3[..., d[1]:], 2: cat_p4[..., d[2]:], 3: self.buf(tag + ".x0n", (1, h32, w32, d[3]))}[i]
                 ops.layernorm(x.view(-1, Cx), nw, nb, 1e-6, out=_rows(dst))
                 feats[i] = dst
-        x2n, x1n, x0n = feats[1], feats[2], feats[3]
+        self._cat = dict(cat_p4=cat_p4, cat_p3=cat_p3, cat_n3=cat_n3, cat_n4=cat_n4)
+        return (feats[1], feats[2], feats[3]), {"feat": feats[2], "h": h16, "w": w16}
+
+    def neck(self, feats, tag="cur"):
+        """YOLOPAFPNNEW.forward (yolo_pafpn_new.py:137-155) on the normed ConvNeXt outputs (already sitting in their
+        concat slots)."""
+        P, d = self.P, self.dims
+        x2n, x1n, x0n = feats
+        cat_p4, cat_p3, cat_n3, cat_n4 = (self._cat[k] for k in ("cat_p4", "cat_p3", "cat_n3", "cat_n4"))
+        h8, w8 = x2n.shape[1:3]
+        h16, w16 = x1n.shape[1:3]
+        h32, w32 = x0n.shape[1:3]
         # top-down
         fpn_out0 = self.conv_gn(x0n, P["lateral_conv0"], cat_n4[..., d[2]:])
         ops.copy_upsample(fpn_out0, cat_p4[..., :d[2]], 2)
@@ -284,7 +315,7 @@ class UnicornEngine:
         pan_out0 = self.csp(cat_n4, P["C3_n4"], self.buf(tag + ".pan_out0", (1, h32, w32, d[3])), tag + ".C3_n4")
         self.dbg = dict(x2n=x2n, x1n=x1n, x0n=x0n, fpn_out0=fpn_out0, f_out0=f_out0, fpn_out1=fpn_out1, pan_out2=pan_out2,
                         pan_out1=pan_out1, pan_out0=pan_out0)
-        return (pan_out2, pan_out1, pan_out0), {"feat": x1n, "h": h16, "w": w16}
+        return (pan_out2, pan_out1, pan_out0)
 
     # ------------------------------------------------------------------------------------------ interaction
     def pos_tokens(self, h, w):

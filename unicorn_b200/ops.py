@@ -113,11 +113,17 @@ def pack_dw_weight(w):
 
 
 def stem_ln(img, w48, bias, lnw, lnb, eps=1e-6):
-    B, _, H, W = img.shape
+    """img: fp32 NCHW [B,3,H,W] or uint8 NHWC [B,H,W,3] (BGR)."""
+    u8 = img.dtype == torch.uint8
+    if u8:
+        B, H, W, _ = img.shape
+    else:
+        B, _, H, W = img.shape
+        assert img.dtype == torch.float32
+    assert img.is_contiguous()
     C0 = w48.shape[1]
-    assert img.dtype == torch.float32 and img.is_contiguous()
     out = torch.empty(B, H // 4, W // 4, C0, dtype=torch.bfloat16, device=img.device)
-    _lib.check(_L().uc_stem_ln(_p(img), _p(w48), _p(bias), _p(lnw), _p(lnb), _p(out), B, H, W, C0, _f(eps), _S()), "uc_stem_ln")
+    _lib.check(_L().uc_stem_ln(_p(img), int(u8), _p(w48), _p(bias), _p(lnw), _p(lnb), _p(out), B, H, W, C0, _f(eps), _S()), "uc_stem_ln")
     return out
 
 

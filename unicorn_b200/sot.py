@@ -22,15 +22,19 @@ def get_label_map(box_xyxy, H, W, device):
     return labels
 
 
-def preprocess(img_rgb, input_size):
-    """PreprocessorX.process (unicorn_sot.py:114-123): RGB uint8 HWC -> BGR fp32 letterboxed (pad 114) [1,3,H,W], r."""
+def preprocess(img_rgb, input_size, out=None):
+    """PreprocessorX.process (unicorn_sot.py:114-123): RGB uint8 HWC -> BGR letterboxed (pad 114), kept as uint8 HWC
+    [1,H,W,3] (the float conversion and the HWC->CHW permute happen inside the stem kernel; values are identical to the
+    reference's float tensor because cv2.resize already returns uint8).  Returns (tensor, r)."""
     import cv2
     height, width = img_rgb.shape[:2]
     r = min(input_size[0] / height, input_size[1] / width)
     rsz = cv2.resize(cv2.cvtColor(img_rgb, cv2.COLOR_RGB2BGR), (int(width * r), int(height * r)), interpolation=cv2.INTER_LINEAR)
-    out = np.full((1, 3, input_size[0], input_size[1]), 114, dtype=np.float32)
-    out[0, :, :int(height * r), :int(width * r)] = rsz.transpose(2, 0, 1)
-    return torch.from_numpy(out), r
+    if out is None:
+        out = torch.empty(1, input_size[0], input_size[1], 3, dtype=torch.uint8).pin_memory()
+    out.fill_(114)
+    out[0, :int(height * r), :int(width * r)] = torch.from_numpy(rsz)
+    return out, r
 
 
 class UnicornSOTTrack:
@@ -45,6 +49,8 @@ class UnicornSOTTrack:
         H, W = self.input_size
         dev = engine.dev
         self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+        self.img_in_u8 = torch.empty(1, H, W, 3, dtype=torch.uint8, device=dev)
+        self._u8 = False
         A = (H // 8) * (W // 8) + (H // 16) * (W // 16) + (H // 32) * (W // 32)
         self.ws = ops.PostWorkspace(A, dev)
         self.host_dets = torch.empty(max_inst, 7, dtype=torch.float32).pin_memory()
@@ -58,21 +64,31 @@ class UnicornSOTTrack:
     def _frame(self):
         e = self.eng
         e.begin_frame()
-        fpn, seq = e.backbone(self.img_in, tag="cur")
-        f_pre, f_cur = e.interaction(self.ref_feat, seq["feat"], cache_ref=True)
-        e_pre, e_cur = e.upsample(f_pre, "embp"), e.upsample(f_cur, "embc")
-        priors = e.propagate(e_pre, e_cur, self.lbs_pre)
+        def correlate(seq):  # runs on a second stream while the neck runs on the main one
+            f_pre, f_cur = e.interaction(self.ref_feat, seq["feat"], cache_ref=True)
+            e_pre, e_cur = e.upsample(f_pre, "embp"), e.upsample(f_cur, "embc")
+            return f_pre, f_cur, e_pre, e_cur, e.propagate(e_pre, e_cur, self.lbs_pre)
+
+        fpn, seq, (f_pre, f_cur, e_pre, e_cur, priors) = e.backbone(self.img_in_u8 if self._u8 else self.img_in, tag="cur", side=correlate)
         out = e.head(fpn, priors, "sot")
         ops.postprocess_device(out[0], 1, self.confthre, self.nmsthre, self.ws, max_keep=self.nms_keep)
         self.last = dict(fpn=fpn, feat=seq["feat"], inter_pre=f_pre, inter_cur=f_cur, embed_pre=e_pre, embed_cur=e_cur, priors=priors, head=out)
 
+    def _stage_input(self, frame):
+        """fp32 [1,3,H,W] (PreprocessorX format) or uint8 [1,H,W,3] (letterboxed BGR frame, 4x fewer H2D bytes)."""
+        u8 = frame.dtype == torch.uint8
+        if u8 != self._u8:
+            self._u8, self.graph = u8, None  # the captured graph reads one of the two static input buffers
+        (self.img_in_u8 if u8 else self.img_in).copy_(frame, non_blocking=True)
+        return self.img_in_u8 if u8 else self.img_in
+
     def initialize_tensor(self, ref_frame, init_box_xyxy):
-        """ref_frame: preprocessed fp32 [1,3,H,W] (host or device); init box in resized-image coordinates."""
+        """ref_frame: preprocessed fp32 [1,3,H,W] or uint8 [1,H,W,3] (host or device); init box in resized-image coordinates."""
         e = self.eng
         H, W = self.input_size
-        self.img_in.copy_(ref_frame, non_blocking=True)
+        inp = self._stage_input(ref_frame)
         e.begin_frame()
-        _, seq = e.backbone(self.img_in, tag="ref")
+        _, seq = e.backbone(inp, tag="ref")
         self.ref_feat = seq["feat"]
         h, w = seq["h"], seq["w"]
         n = h * w
@@ -87,7 +103,7 @@ class UnicornSOTTrack:
     def track_tensor(self, cur_frame):
         """cur_frame: preprocessed fp32 [1,3,H,W], ideally pinned host memory.  Returns (dets[:max_inst] cpu, count)."""
         self.frame_id += 1
-        self.img_in.copy_(cur_frame, non_blocking=True)
+        self._stage_input(cur_frame)
         if not self.use_graph:
             self._frame()
         elif self.graph is None:
@@ -119,7 +135,7 @@ class UnicornSOTTrack:
 
     def track(self, image, info: dict = None):
         cur, r = preprocess(image, self.input_size)
-        dets, n = self.track_tensor(cur.pin_memory())
+        dets, n = self.track_tensor(cur)
         if n > 0:
             out = dets.numpy().copy()
             out[:, 0:4:2] = out[:, 0:4:2].clip(0, self.input_size[1])
