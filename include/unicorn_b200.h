@@ -155,10 +155,12 @@ UC_API int uc_head_decode(const float* const* regobj, const float* const* cls, c
 /* postprocess (utils/boxes.py:33-77) on the device: out_dets f32 [<=A, 7] rows (x1,y1,x2,y2,obj,cls_conf,cls_id)
  * in descending score order, *out_count (device int) = number of rows.  max_keep > 0 stops the greedy scan once that
  * many boxes are kept: the rows returned are exactly the first max_keep rows of the full result (the SOT driver only
- * consumes output[:max_inst], external/lib/test/tracker/unicorn_sot.py:69-70); max_keep <= 0 = no limit. */
+ * consumes output[:max_inst], external/lib/test/tracker/unicorn_sot.py:69-70); max_keep <= 0 = no limit.
+ * out_anchor (device int[A], may be NULL) receives the anchor index of every returned row — what postprocess_inst
+ * (utils/boxes.py:125-128) needs to pick each instance's location / dynamic parameters / FPN level. */
 UC_API long uc_postprocess_workspace_bytes(int max_anchors);
 UC_API int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, int max_keep, void* workspace,
-                          long workspace_bytes, float* out_dets, int* out_count, void* stream);
+                          long workspace_bytes, float* out_dets, int* out_count, int* out_anchor, void* stream);
 
 /* Instance-embedding sampling at box centres (unicorn/evaluators/mot_evaluator.py:1024-1034): embed NHWC 16-bit
  * [h,w,C] (pixel stride ld), boxes f32 [n,ldb] xyxy in network-input pixels, stride = 8; grid_sample(bilinear,
@@ -174,6 +176,18 @@ UC_API int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, int N
  * (quasi_dense_embed_tracker.py:80,146); plus_one = 1: cython_bbox.bbox_overlaps' inclusive-pixel convention
  * (unicorn/tracker/matching.py:65-68, ByteTrack). */
 UC_API int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, int plus_one, void* stream);
+
+/* dst += aligned_bilinear(src, factor) on NHWC bf16 maps (condinst/comm.py:5-27; mask_branch.py:81-96). */
+UC_API int uc_aligned_bilinear_add(const void* src, int lds, int hs, int ws, void* dst, int ldd, int C, int factor, void* stream);
+/* Per-instance CondInst masks (condinst/dynamic_mask_head.py:61-87,159-225,284; utils/boxes.py:138-145) for the first
+ * min(*count_dev, n_max) rows of the NMS output: mask_feats f32 [h,w,8], up_masks f32 [h,w,9*up_rate^2],
+ * dyn_levels = HOST array of 3 device pointers to the controller outputs [h_k*w_k, ld_dyn] (169 used), level_hw /
+ * level_strides / level_soi host arrays; anchors_dev = out_anchor of uc_postprocess; scratch >= n_max*h*w*(1+up^2)
+ * floats; out_masks f32 [n_max, h*up*d, w*up*d] = sigmoid scores. */
+UC_API int uc_dynamic_masks(const float* mask_feats, const float* up_masks, int h, int w, int up_rate, int d_rate,
+                            const float* const* dyn_levels, int ld_dyn, const int* level_hw, const int* level_strides,
+                            const float* level_soi, const int* anchors_dev, const int* count_dev, int n_max, float* scratch,
+                            float* out_masks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -379,3 +379,104 @@ class SOTOracle:
             stages.update(fpn=fpn, feat=cur["feat"], pos=cur["pos"], inter_pre=f_pre, inter_cur=f_cur, embed_pre=e_pre,
                           embed_cur=e_cur, coarse=coarse, head=out, dets=dets)
         return dets
+
+
+# ----------------------------------------------------------------------------------------------- mask head (config 4)
+def aligned_bilinear(t, factor):
+    """condinst/comm.py:5-27 (== utils/boxes.py:212-234)."""
+    if factor == 1:
+        return t
+    h, w = t.shape[2:]
+    t = F.pad(t, pad=(0, 1, 0, 1), mode="replicate")
+    oh, ow = factor * h + 1, factor * w + 1
+    t = F.interpolate(t, size=(oh, ow), mode="bilinear", align_corners=True)
+    t = F.pad(t, pad=(factor // 2, 0, factor // 2, 0), mode="replicate")
+    return t[:, :, :oh - 1, :ow - 1]
+
+
+def _conv_gn_relu(x, sd, p):
+    """conv_with_kaiming_uniform("BN", activation=True) after BN->GN16 (eps 1e-3): conv3x3 (no bias) -> GN -> ReLU
+    (condinst/conv_with_kaiming_uniform.py:8-50, exp/unicorn_track.py:118-122,450-470)."""
+    x = F.conv2d(x, sd[p + "0.weight"], None, padding=1)
+    return F.relu(F.group_norm(x, 16, sd[p + "1.weight"], sd[p + "1.bias"], 1e-3))
+
+
+def mask_branch(fpn, sd, p="head.mask_branch."):
+    """MaskBranch.forward, use_raft=True (condinst/mask_branch.py:77-96,158-162) -> (mask_feats (1,8,h,w), up_masks (1,144,h,w))."""
+    x = _conv_gn_relu(fpn[0], sd, p + "refine.0.")
+    for i in (1, 2):
+        xp = _conv_gn_relu(fpn[i], sd, p + f"refine.{i}.")
+        x = x + aligned_bilinear(xp, x.shape[2] // xp.shape[2])
+    t = x
+    for i in range(4):
+        t = _conv_gn_relu(t, sd, p + f"tower.{i}.")
+    mask_feats = F.conv2d(t, sd[p + "tower.4.weight"], sd[p + "tower.4.bias"])
+    u = F.relu(F.conv2d(x, sd[p + "up_mask_layer.0.weight"], sd[p + "up_mask_layer.0.bias"], padding=1))
+    up_masks = F.conv2d(u, sd[p + "up_mask_layer.2.weight"], sd[p + "up_mask_layer.2.bias"])
+    return mask_feats, up_masks
+
+
+def head_forward_mask(fpn, priors, sd, cfg, mode):
+    """UnicornHeadMask.forward eval (unicorn_head_mask.py:280-343,451-471) + decode_outputs (:502-519).
+    Returns outputs (1,A,5+ncls), locations (A,2), dynamic_params (1,A,169), fpn_levels (1,A), mask_feats, up_masks."""
+    out, reg_feats = head_forward(fpn, priors, sd, cfg, mode, decode=True, return_feats=True)
+    dyn, lvls, locs = [], [], []
+    for k in range(3):
+        d = F.conv2d(reg_feats[k], sd[f"head.controllers.{k}.weight"], sd[f"head.controllers.{k}.bias"], padding=1)
+        dyn.append(d.flatten(-2).permute(0, 2, 1))
+        lvls.append(torch.full((1, d.shape[2] * d.shape[3]), k))
+        hs, ws = d.shape[-2:]
+        yv, xv = torch.meshgrid(torch.arange(hs), torch.arange(ws), indexing="ij")
+        locs.append((torch.stack((xv, yv), 2).view(-1, 2).float() + 0.5) * STRIDES[k])
+    mf, um = mask_branch(fpn, sd)
+    return out, torch.cat(locs, 0), torch.cat(dyn, 1), torch.cat(lvls, 1), mf, um
+
+
+def dynamic_masks(mask_feats, params, inst_locs, inst_levels, up_masks, up_rate=4, soi=(64.0, 128.0, 256.0, 512.0, 1024.0)):
+    """DynamicMaskHead.__call__ eval (condinst/dynamic_mask_head.py:172-225,159-170,284): -> (N,1,up*h,up*w) sigmoid."""
+    _, C, H, W = mask_feats.shape
+    n = params.shape[0]
+    sx = torch.arange(0, W * 8, step=8, dtype=torch.float32)
+    sy = torch.arange(0, H * 8, step=8, dtype=torch.float32)
+    yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+    locations = torch.stack((xx.reshape(-1), yy.reshape(-1)), dim=1) + 4  # compute_locations (comm.py:30-45)
+    rel = (inst_locs.reshape(-1, 1, 2) - locations.reshape(1, -1, 2)).permute(0, 2, 1).float()
+    rel = rel / torch.tensor(soi)[inst_levels.long()].reshape(-1, 1, 1)
+    x = torch.cat([rel, mask_feats[0].reshape(1, C, H * W).expand(n, -1, -1)], dim=1)  # (N,10,HW)
+    w0, w1, w2, b0, b1, b2 = torch.split_with_sizes(params, [80, 64, 8, 8, 8, 1], dim=1)  # parse_dynamic_params :61-87
+    x = F.relu(torch.bmm(w0.reshape(n, 8, 10), x) + b0.reshape(n, 8, 1))
+    x = F.relu(torch.bmm(w1.reshape(n, 8, 8), x) + b1.reshape(n, 8, 1))
+    logits = (torch.bmm(w2.reshape(n, 1, 8), x) + b2.reshape(n, 1, 1)).reshape(n, 1, H, W)
+    m = torch.softmax(up_masks.view(1, 1, 9, up_rate, up_rate, H, W), dim=2)  # upsample_preds :159-170
+    up = F.unfold(logits, [3, 3], padding=1).view(n, 1, 9, 1, 1, H, W)
+    up = torch.sum(m * up, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(n, 1, up_rate * H, up_rate * W)
+    return up.sigmoid()
+
+
+def postprocess_inst(pred, locations, dyn, levels, mask_feats, up_masks, num_classes, conf_thre, nms_thre, d_rate=2, max_masks=None):
+    """utils/boxes.py:80-152 for one image: (dets (M,7), masks (min(M,max_masks),1,H,W)); max_masks limits how many
+    of the (score-ordered) instances get a mask (the VOS driver only reads the first, unicorn_vos.py:121-149)."""
+    p = pred.clone()
+    box = p.new_zeros(p.shape)
+    box[:, :, 0] = p[:, :, 0] - p[:, :, 2] / 2
+    box[:, :, 1] = p[:, :, 1] - p[:, :, 3] / 2
+    box[:, :, 2] = p[:, :, 0] + p[:, :, 2] / 2
+    box[:, :, 3] = p[:, :, 1] + p[:, :, 3] / 2
+    p[:, :, :4] = box[:, :, :4]
+    ip = p[0]
+    cc, cp = torch.max(ip[:, 5:5 + num_classes], 1, keepdim=True)
+    mask = ip[:, 4] * cc.squeeze(1) >= conf_thre
+    det = torch.cat((ip[:, :5], cc, cp.float()), 1)[mask]
+    if det.shape[0] == 0:
+        return None, None
+    scores = (det[:, 4] * det[:, 5]).numpy()
+    keep_all = []
+    for c in np.unique(det[:, 6].numpy()):
+        idx = np.nonzero(det[:, 6].numpy() == c)[0]
+        keep_all.append(idx[nms_greedy(det[idx, :4].numpy(), scores[idx], nms_thre)])
+    keep = np.concatenate(keep_all)
+    keep = torch.from_numpy(keep[np.argsort(-scores[keep], kind="stable")])
+    det = det[keep]
+    k = keep if max_masks is None else keep[:max_masks]
+    masks = dynamic_masks(mask_feats, dyn[0][mask][k], locations[mask][k], levels[0][mask][k], up_masks, up_rate=8 // d_rate)
+    return det, aligned_bilinear(masks, d_rate)

@@ -185,10 +185,12 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restr
 // halo) in shared memory by cp.async; out-of-map halo pixels are zero-filled.  The LayerNorm that follows in the
 // ConvNeXt block runs as uc_layernorm on the (L2-resident) result.  x, y NHWC bf16 [B,H,W,C]; w [49][C] fp32.
 template <int CCH>
-__global__ void __launch_bounds__(256) dwconv7_tiled_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, uint16_t* __restrict__ y, int H,
-                                                             int W, int C, int tiles_w) {
-  constexpr int TW = 16, PAIRS = CCH / 2, TH = 256 / PAIRS, HW_ = TW + 6, HH_ = TH + 6;
+__global__ void __launch_bounds__(512, 2) dwconv7_tiled_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, uint16_t* __restrict__ y, int H,
+                                                                int W, int C, int tiles_w) {
+  // 512 threads = (CCH/2 channel pairs) x (TH rows) x (2 half rows of 8 pixels): 16 accumulators + 14 staged inputs per
+  // thread stay in registers (a 16-pixel strip per thread made the compiler re-read shared memory for every tap).
+  constexpr int TW = 16, PX = 8, PAIRS = CCH / 2, TH = 512 / (PAIRS * 2), HW_ = TW + 6, HH_ = TH + 6;
   constexpr int PIX_BYTES = CCH * 2, CHUNKS = PIX_BYTES / 16;
   extern __shared__ __align__(16) uint8_t dsm[];
   uint8_t* tile = dsm;                                             // [HH_][HW_][CCH] bf16
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) dwconv7_tiled_kernel(const uint16_t* __re
   const int c0 = blockIdx.y * CCH;
   const int ow0 = (blockIdx.x % tiles_w) * TW, oh0 = (blockIdx.x / tiles_w) * TH;
   const uint16_t* xb = x + static_cast<long>(b) * H * W * C;
-  for (int i = threadIdx.x; i < HH_ * HW_ * CHUNKS; i += 256) {
+  for (int i = threadIdx.x; i < HH_ * HW_ * CHUNKS; i += 512) {
     const int ch = i % CHUNKS, px = i / CHUNKS;
     const int hx = px % HW_, hy = px / HW_;
     const int ih = oh0 + hy - 3, iw = ow0 + hx - 3;
@@ -209,41 +211,49 @@ __global__ void __launch_bounds__(256) dwconv7_tiled_kernel(const uint16_t* __re
       *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  for (int i = threadIdx.x; i < 49 * CCH; i += 256) sw[i] = __ldg(w + static_cast<long>(i / CCH) * C + c0 + (i % CCH));
+  for (int i = threadIdx.x; i < 49 * CCH; i += 512) sw[i] = __ldg(w + static_cast<long>(i / CCH) * C + c0 + (i % CCH));
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int cp = threadIdx.x % PAIRS, r = threadIdx.x / PAIRS;
-  float a0[TW], a1[TW];
+  const int cp = threadIdx.x % PAIRS;
+  const int hx = (threadIdx.x / PAIRS) & 1, r = threadIdx.x / (PAIRS * 2);
+  // accumulators and operands are (channel 2cp, channel 2cp+1) pairs: one packed fma.rn.f32x2 (Blackwell FFMA2) per tap
+  // and pixel instead of two scalar FMAs — the kernel is instruction-issue bound.
+  unsigned long long acc[PX];
   {
     const float b0 = __ldg(bias + c0 + 2 * cp), b1 = __ldg(bias + c0 + 2 * cp + 1);
+    const unsigned long long bb = (static_cast<unsigned long long>(__float_as_uint(b1)) << 32) | __float_as_uint(b0);
 #pragma unroll
-    for (int p = 0; p < TW; ++p) { a0[p] = b0; a1[p] = b1; }
+    for (int p = 0; p < PX; ++p) acc[p] = bb;
   }
 #pragma unroll 1
   for (int kh = 0; kh < 7; ++kh) {
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + (r + kh) * HW_ * PIX_BYTES) + cp;
-    float v0[HW_], v1[HW_];
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + ((r + kh) * HW_ + hx * PX) * PIX_BYTES) + cp;
+    unsigned long long v[PX + 6];
 #pragma unroll
-    for (int j = 0; j < HW_; ++j) {
+    for (int j = 0; j < PX + 6; ++j) {
       const uint32_t u = rowp[j * (PIX_BYTES / 4)];
-      v0[j] = bf16lo(u); v1[j] = bf16hi(u);
+      v[j] = (static_cast<unsigned long long>(u & 0xffff0000u) << 32) | (u << 16);  // (lo -> .x, hi -> .y) as fp32 bits
     }
 #pragma unroll
     for (int kw = 0; kw < 7; ++kw) {
-      const float2 wv = *reinterpret_cast<const float2*>(sw + (kh * 7 + kw) * CCH + 2 * cp);
+      const unsigned long long wv = *reinterpret_cast<const unsigned long long*>(sw + (kh * 7 + kw) * CCH + 2 * cp);
 #pragma unroll
-      for (int p = 0; p < TW; ++p) {
-        a0[p] = fmaf(v0[p + kw], wv.x, a0[p]);
-        a1[p] = fmaf(v1[p + kw], wv.y, a1[p]);
-      }
+      for (int p = 0; p < PX; ++p) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[p]) : "l"(v[p + kw]), "l"(wv));
     }
+  }
+  float a0[PX], a1[PX];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    a0[p] = __uint_as_float(static_cast<uint32_t>(acc[p] & 0xffffffffull));
+    a1[p] = __uint_as_float(static_cast<uint32_t>(acc[p] >> 32));
   }
   const int oh = oh0 + r;
   if (oh < H) {
     uint32_t* yr = reinterpret_cast<uint32_t*>(y + (static_cast<long>(b) * H + oh) * W * C + c0) + cp;
 #pragma unroll
-    for (int p = 0; p < TW; ++p) {
-      if (ow0 + p < W) yr[static_cast<long>(ow0 + p) * (C / 2)] = pack_bf16(a0[p], a1[p]);
+    for (int p = 0; p < PX; ++p) {
+      const int ow = ow0 + hx * PX + p;
+      if (ow < W) yr[static_cast<long>(ow) * (C / 2)] = pack_bf16(a0[p], a1[p]);
     }
   }
 }
@@ -411,11 +421,11 @@ extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bia
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(dwconv7_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     dim3 grid(tiles_w * ((H + 7) / 8), C / 64, B);
-    dwconv7_tiled_kernel<64><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    dwconv7_tiled_kernel<64><<<grid, 512, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
   } else {
     constexpr int smem = (16 + 6) * 22 * 64 + 49 * 32 * 4;
     dim3 grid(tiles_w * ((H + 15) / 16), C / 32, B);
-    dwconv7_tiled_kernel<32><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    dwconv7_tiled_kernel<32><<<grid, 512, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
   }
   return check_launch("uc_dwconv7");
 }

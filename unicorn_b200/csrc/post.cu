@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(DecodeLevels lv, float
 // det rows: x1,y1,x2,y2,obj,class_conf,class_pred ; key = (score bits << 32) | (0xffffffff - candidate index)
 __global__ void __launch_bounds__(1024) det_filter_kernel(const float* __restrict__ pred, int A, int ncls, float conf,
                                                            float* __restrict__ det, unsigned long long* __restrict__ keys,
-                                                           int* __restrict__ count, int cap) {
+                                                           int* __restrict__ count, int cap, int* __restrict__ det_anchor) {
   __shared__ int warp_cnt[32];
   __shared__ int warp_excl[32];
   __shared__ int base, round_total;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(1024) det_filter_kernel(const float* __restric
 #pragma unroll
         for (int t = 0; t < 7; ++t) d[t] = r[t];
         keys[idx] = (static_cast<unsigned long long>(__float_as_uint(score)) << 32) | (0xffffffffu - static_cast<unsigned>(idx));
+        det_anchor[idx] = a;
       }
     }
     __syncthreads();
@@ -121,10 +122,12 @@ __global__ void __launch_bounds__(1024) sort_desc_kernel(unsigned long long* __r
 
 // ---- gather rows in sorted order
 __global__ void __launch_bounds__(256) det_gather_kernel(const float* __restrict__ det, const unsigned long long* __restrict__ keys,
-                                                          const int* __restrict__ count, float* __restrict__ sorted) {
+                                                          const int* __restrict__ count, float* __restrict__ sorted,
+                                                          const int* __restrict__ det_anchor, int* __restrict__ sorted_anchor) {
   const int n = *count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned idx = 0xffffffffu - static_cast<unsigned>(keys[i] & 0xffffffffull);
+    sorted_anchor[i] = det_anchor[idx];
 #pragma unroll
     for (int t = 0; t < 7; ++t) sorted[static_cast<long>(i) * 7 + t] = det[static_cast<long>(idx) * 7 + t];
   }
@@ -150,7 +153,8 @@ __device__ __forceinline__ bool nms_hit(const float4 a, const float4 b, float th
 }
 
 __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restrict__ sorted, const int* __restrict__ count, float thr,
-                                                           float* __restrict__ out, int* __restrict__ out_count, int max_keep) {
+                                                           float* __restrict__ out, int* __restrict__ out_count, int max_keep,
+                                                           const int* __restrict__ sorted_anchor, int* __restrict__ out_anchor) {
   extern __shared__ float4 kept_box[];                       // [kNmsKeepSmem]
   float* kept_cls = reinterpret_cast<float*>(kept_box + kNmsKeepSmem);  // [kNmsKeepSmem]
   __shared__ float4 cbox[kNmsChunk];
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restric
         float* o = out + static_cast<long>(pos) * 7;
 #pragma unroll
         for (int q = 0; q < 7; ++q) o[q] = d[q];
+        if (out_anchor) out_anchor[pos] = sorted_anchor[c0 + tid];
       }
     }
     __syncthreads();
@@ -270,11 +275,11 @@ extern "C" long uc_postprocess_workspace_bytes(int max_anchors) {
   const long A = max_anchors;
   long a2 = 1;
   while (a2 < A) a2 <<= 1;
-  return A * 7 * 4 * 2 + a2 * 8 + 256;
+  return A * 7 * 4 * 2 + a2 * 8 + A * 4 * 2 + 256;
 }
 
 extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thre, float nms_thre, int max_keep, void* workspace,
-                              long workspace_bytes, float* out_dets, int* out_count, void* stream_v) {
+                              long workspace_bytes, float* out_dets, int* out_count, int* out_anchor, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!pred || !workspace || !out_dets || !out_count || A < 1 || ncls < 1) return set_error(UC_EINVAL, "uc_postprocess: bad arguments");
   if (workspace_bytes < uc_postprocess_workspace_bytes(A)) return set_error(UC_EINVAL, "uc_postprocess: workspace too small");
@@ -285,15 +290,18 @@ extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thr
   float* det = reinterpret_cast<float*>(ws + 256);
   float* sorted = det + static_cast<long>(A) * 7;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sorted + static_cast<long>(A) * 7);
-  det_filter_kernel<<<1, 1024, 0, stream>>>(pred, A, ncls, conf_thre, det, keys, count, A);
+  int* det_anchor = reinterpret_cast<int*>(keys + a2);
+  int* sorted_anchor = det_anchor + A;
+  det_filter_kernel<<<1, 1024, 0, stream>>>(pred, A, ncls, conf_thre, det, keys, count, A, det_anchor);
   sort_desc_kernel<<<1, 1024, 0, stream>>>(keys, count, static_cast<int>(a2));
-  det_gather_kernel<<<std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream>>>(det, keys, count, sorted);
+  det_gather_kernel<<<std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream>>>(det, keys, count, sorted, det_anchor, sorted_anchor);
   constexpr int smem = kNmsKeepSmem * (16 + 4);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count, max_keep > 0 ? max_keep : 0x7fffffff);
+  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count, max_keep > 0 ? max_keep : 0x7fffffff,
+                                               sorted_anchor, out_anchor);
   return check_launch("uc_postprocess");
 }

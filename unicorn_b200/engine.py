@@ -49,6 +49,7 @@ class UnicornEngine:
         self._pos_cache = {}
         self._side_streams = None
         self._fork_stream = None
+        self._with_masks = False
         self._bn_cache = {}
         self._bn_dirty = False
         self.autotune = autotune
@@ -121,7 +122,18 @@ class UnicornEngine:
                 cb = torch.zeros(8, device=dev)
                 cb[:cw.shape[0]] = sd[h + f"cls_preds{sfx}.{k}.bias"].to(dev)
                 lvl["pred" + sfx] = (ops.pack_conv_weight(ro_w), ro_b, ops.pack_conv_weight(cw), cb, cw.shape[0])
+            if self.cfg["mask"]:  # controller conv3x3 256 -> 169 dynamic-conv parameters (unicorn_head_mask.py:238-247,333-334)
+                cb = torch.zeros(176, device=dev)
+                cb[:169] = sd[h + f"controllers.{k}.bias"].to(dev)
+                lvl["ctrl"] = (pw(h + f"controllers.{k}.weight"), cb)
             P["head"].append(lvl)
+        if self.cfg["mask"]:  # MaskBranch (condinst/mask_branch.py:17-70), BN -> GN16 eps 1e-3, ReLU
+            mb = h + "mask_branch."
+            cgr = lambda p: _ConvGN(pw(p + "0.weight"), f(p + "1.weight"), f(p + "1.bias"), 3, 1)  # noqa: E731
+            P["mask"] = dict(refine=[cgr(mb + f"refine.{k}.") for k in range(3)], tower=[cgr(mb + f"tower.{i}.") for i in range(4)],
+                             out=(pw(mb + "tower.4.weight"), f(mb + "tower.4.bias")),
+                             up0=(pw(mb + "up_mask_layer.0.weight"), f(mb + "up_mask_layer.0.bias")),
+                             up2=(pw(mb + "up_mask_layer.2.weight"), f(mb + "up_mask_layer.2.bias")))
         self.P = P
 
     # ------------------------------------------------------------------------------------------ buffers
@@ -386,10 +398,31 @@ class UnicornEngine:
         return (c0, c1, c2)
 
     # ------------------------------------------------------------------------------------------ head
-    def head(self, fpn, priors, mode):
+    def mask_branch(self, fpn):
+        """MaskBranch.forward with use_raft (condinst/mask_branch.py:77-96,158-162): -> (mask_feats fp32 [1,h8,w8,8],
+        up_masks fp32 [1,h8,w8,144])."""
+        M = self.P["mask"]
+        _, h, w, _ = fpn[0].shape
+        x = self.conv_gn(fpn[0], M["refine"][0], self.buf("mask.x", (1, h, w, 128)), act=ACT_RELU)
+        for i in (1, 2):
+            _, hi, wi, _ = fpn[i].shape
+            xp = self.conv_gn(fpn[i], M["refine"][i], self.buf(f"mask.r{i}", (1, hi, wi, 128)), act=ACT_RELU)
+            ops.aligned_bilinear_add(xp, x, h // hi)
+        t = x
+        for i in range(4):
+            t = self.conv_gn(t, M["tower"][i], self.buf(f"mask.t{i % 2}", (1, h, w, 128)), act=ACT_RELU)
+        mf = self.conv(t, M["out"][0], 1, bias=M["out"][1], out=self.buf("mask.feats", (1, h, w, 8), F32))
+        u = self.conv(x, M["up0"][0], 3, 1, 1, bias=M["up0"][1], act=ACT_RELU, out=self.buf("mask.u0", (1, h, w, 128)))
+        um = self.conv(u, M["up2"][0], 1, bias=M["up2"][1], out=self.buf("mask.up", (1, h, w, 144), F32))
+        return mf, um
+
+    def head(self, fpn, priors, mode, with_masks=False):
         """UnicornHead.forward eval branch (unicorn_head.py:267-336) + decode_outputs (:467-482).
         fpn: 3 NHWC bf16 maps; priors: 3 fp32 [1,h,w] maps or None (MOT: zero prior == no fusion term).
-        Returns fp32 [1, A, 5+ncls_mode]."""
+        Returns fp32 [1, A, 5+ncls_mode].  with_masks=True (UnicornHeadMask, unicorn_head_mask.py:333-343) also runs the
+        controller convs; their outputs are left in self.dyn_levels (3 x fp32 [1,h,w,176]) for ops.dynamic_masks."""
+        self._with_masks = with_masks
+        self.dyn_levels = [None] * 3
         sfx = "_sot" if mode == "sot" else ""
         ro_outs, cls_outs, hw = [None] * 3, [None] * 3, [None] * 3
         ncls = 1 if mode == "sot" else self.ncls
@@ -428,6 +461,9 @@ class UnicornEngine:
             cls_outs[k] = ops.conv2d(feats[0], cw, 1, 1, bias=cb, out=self.buf(f"head{k}.clso", (1, h, w, 8), F32))
             ro_outs[k] = ops.conv2d(feats[1], row, 1, 1, bias=rob, out=self.buf(f"head{k}.roo", (1, h, w, 8), F32))
             hw[k] = (h, w)
+            if self._with_masks:
+                cw_, cb_ = L["ctrl"]
+                self.dyn_levels[k] = self.conv(feats[1], cw_, 3, 1, 1, bias=cb_, out=self.buf(f"head{k}.dyn", (1, h, w, 176), F32))
 
 
 def _rows(t):

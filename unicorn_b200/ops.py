@@ -273,6 +273,7 @@ class PostWorkspace:
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.dets = torch.empty(max_anchors, 7, dtype=torch.float32, device=device)
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.anchors = torch.zeros(max_anchors, dtype=torch.int32, device=device)
         self.max_anchors = max_anchors
 
 
@@ -281,7 +282,7 @@ def postprocess_device(pred, ncls, conf, nms, ws, max_keep=0):
     max_keep > 0 returns exactly the first max_keep rows of the full NMS result."""
     A = pred.shape[0]
     assert pred.is_contiguous() and pred.dtype == torch.float32 and A <= ws.max_anchors
-    _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), int(max_keep), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _S()),
+    _lib.check(_L().uc_postprocess(_p(pred), A, ncls, _f(conf), _f(nms), int(max_keep), _p(ws.buf), _l(ws.nbytes), _p(ws.dets), _p(ws.count), _p(ws.anchors), _S()),
                "uc_postprocess", 4)
     return ws.dets, ws.count
 
@@ -311,4 +312,30 @@ def box_iou(a, b, plus_one=False):
     out = torch.empty(N, M, dtype=torch.float32, device=a.device)
     if N and M:
         _lib.check(_L().uc_box_iou(_p(a), a.stride(0), N, _p(b), b.stride(0), M, _p(out), int(plus_one), _S()), "uc_box_iou")
+    return out
+
+
+def aligned_bilinear_add(src, dst, factor):
+    _, hs, ws, C = src.shape
+    assert dst.shape == (1, hs * factor, ws * factor, C)
+    _lib.check(_L().uc_aligned_bilinear_add(_p(src), _nhwc_ld(src), hs, ws, _p(dst), _nhwc_ld(dst), C, factor, _S()), "uc_aligned_bilinear_add")
+    return dst
+
+
+def dynamic_masks(mask_feats, up_masks, dyn_levels, level_hw, ws, n_max, up_rate=4, d_rate=2, strides=(8, 16, 32), soi=(64.0, 128.0, 256.0),
+                  out=None, scratch=None):
+    """mask_feats fp32 [1,h,w,8]; up_masks fp32 [1,h,w,9*up^2]; dyn_levels: 3 fp32 [1,hk,wk,ld] controller outputs;
+    ws: PostWorkspace after postprocess_device.  Returns fp32 [n_max, h*up*d, w*up*d]."""
+    _, h, w, _ = mask_feats.shape
+    H, W = h * up_rate * d_rate, w * up_rate * d_rate
+    if out is None:
+        out = torch.zeros(n_max, H, W, dtype=torch.float32, device=mask_feats.device)
+    if scratch is None:
+        scratch = torch.empty(n_max * h * w * (1 + up_rate * up_rate), dtype=torch.float32, device=mask_feats.device)
+    dl = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in dyn_levels])
+    hw = (ctypes.c_int * 6)(*[v for pair in level_hw for v in pair])
+    st = (ctypes.c_int * 3)(*strides)
+    so = (ctypes.c_float * 3)(*soi)
+    _lib.check(_L().uc_dynamic_masks(_p(mask_feats), _p(up_masks), h, w, up_rate, d_rate, dl, dyn_levels[0].shape[-1], hw, st, so,
+                                     _p(ws.anchors), _p(ws.count), n_max, _p(scratch), _p(out), _S()), "uc_dynamic_masks", 3)
     return out
