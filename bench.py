@@ -72,6 +72,25 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """CPU threads this process may really use: min(affinity, cgroup CPU quota).  The GPU boxes expose 128 logical
+    CPUs but a 16-CPU cgroup quota; 128 torch threads there are ~20x slower than 16."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(int(q[0]) / int(q[1]))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except Exception:
+            pass
+    return n
+
+
 def run_reference(args):
     """The reference's own algorithm on the host CPU cores (oracle port; see oracle/unicorn_oracle.py header)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -81,7 +100,7 @@ def run_reference(args):
     import unicorn_oracle as orc
     from unicorn_b200.synthetic import make_video
     from unicorn_b200.weights import make_state_dict
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     H, W = args.size
     steps, warm = min(args.steps, 6), min(args.warmup, 1)
@@ -111,7 +130,7 @@ def cpu_baseline_sample(cfg, H, W, budget_s=25.0):
     import unicorn_oracle as orc
     from unicorn_b200.synthetic import make_video
     from unicorn_b200.weights import make_state_dict
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd = make_state_dict(cfg, 0)
     frames, boxes = make_video(4, H, W, seed=0)
@@ -260,6 +279,7 @@ def main():
         out["cpu_baseline"] = cpu_baseline_sample(args.config, H, W)
     else:
         out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (N>1 or --no-cpu-baseline)"}
+        out["cpu_baseline"]["cores"] = host_threads()
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
