@@ -78,7 +78,8 @@ typedef struct UcConv2d {
   void* y;
   int ldy;
   int y_dtype;
-  int block_n; /* 0 = auto; else force the N tile (16,32,64,96,128,192,256) */
+  int block_n; /* 0 = auto; else force the N tile (16,32,64,96,128,192,256); +1000 (1128,1192,1256) = the
+                  cta_group::2 variant: an SM pair computes a 256 x N tile with one pair-MMA stream */
   /* Optional GroupNorm statistics of the (pre-activation) output, accumulated per (image, group):
    * gn_stats[b][g] = {sum, sumsq} as int64 fixed point (value * 2^22; integer atomics => order independent,
    * bit-reproducible); must be zeroed by the caller; NULL = off.  Consumed by uc_groupnorm_apply. */

@@ -25,6 +25,12 @@ CASES = [
 ]
 for bn in (16, 32, 64, 96, 128, 192, 256):
     CASES.append((f"bn{bn}", 1, 1, 640, 320, 768, 1, 1, 0, {"block_n": bn}))
+# 2-CTA cluster variant with weight multicast (odd number of M tiles -> one padding tile; GN; 3x3; residual)
+for bn in (1128, 1192, 1256):
+    CASES.append((f"mc{bn}", 1, 1, 1150, 320, 768, 1, 1, 0, {"block_n": bn, "bias": True, "act": "gelu"}))
+CASES.append(("mc_conv3x3_gn", 1, 26, 40, 256, 256, 3, 1, 1, {"block_n": 1256, "gn": 16}))
+CASES.append(("mc_res_gamma", 1, 1, 777, 768, 192, 1, 1, 0, {"block_n": 1192, "bias": True, "gamma": True, "res": True}))
+CASES.append(("mc_conv3x3_s2", 1, 50, 80, 384, 384, 3, 2, 1, {"block_n": 1128}))
 
 
 def _act(x, name):

@@ -33,6 +33,7 @@ struct ConvTap {
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmBh;  // half-height weight box for the 2-CTA multicast variant
   CUtensorMap tmC;  // output map for the TMA store (16-bit outputs)
   ConvTap taps[kMaxTaps];
   int ntaps, kchunks;
@@ -83,7 +84,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // Epilogue of one 32-column chunk of one tile, specialised on the activation so that the inner loops are branch-free.
 template <int ACT>
 __device__ __forceinline__ void epi_math(float (&f)[32], const ConvKernelParams& p, int cbase, int ncols, bool valid, int b,
-                                         int lane) {
+                                         int lane, bool tile_ok) {
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -112,7 +113,7 @@ __device__ __forceinline__ void epi_math(float (&f)[32], const ConvKernelParams&
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
-          if (lane == 0) {
+          if (lane == 0 && tile_ok) {
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
             atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
             atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
@@ -141,9 +142,15 @@ __device__ __forceinline__ void epi_math(float (&f)[32], const ConvKernelParams&
 // Persistent kernel: grid = min(#tiles, resident CTAs); every CTA walks tiles tile = blockIdx.x + i * gridDim.x (N tile
 // fastest, so CTAs running side by side share the activation tile in L2).  The TMEM accumulator is double buffered:
 // the MMA warp fills accumulator (i+1)&1 while the epilogue warps drain accumulator i&1.
-template <int BLOCK_N, int STAGES>
+// CLUSTER = 2 is the cta_group::2 variant: two CTAs (a cluster = one TPC's SM pair) with consecutive M tiles and the same N
+// tile compute a 256 x BLOCK_N tile with ONE pair-MMA stream issued by the leader CTA.  Each CTA stages its own 128 rows
+// of A and only HALF of the weight box (BLOCK_N/2 rows): shared-memory traffic per MAC (TMA writes + MMA operand reads,
+// which is what bounds the single-CTA kernel on K-deep layers) drops by a third.  Barriers: the leader's full[stage]
+// collects the bytes of all four loads; one tcgen05.commit.cta_group::2 multicast releases the stage / publishes the
+// accumulator in both CTAs; the peer's epilogue warps hand their accumulator back with remote arrives on the leader.
+template <int BLOCK_N, int STAGES, int CLUSTER>
 __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
+  constexpr int B_BYTES = (BLOCK_N / CLUSTER) * kBlockK * 2;  // per-CTA weight bytes per stage
   constexpr uint32_t ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr int C_BLOCKS = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;  // 64-channel staging blocks for the TMA store
@@ -160,7 +167,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kiters = p.ntaps * p.kchunks;
-  const int num_tiles = p.n_tiles * p.m_tiles;
+  const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  // work items: (N tile, group of CLUSTER consecutive M tiles); this CTA takes M tile group*CLUSTER + crank
+  const int num_items = p.n_tiles * ((p.m_tiles + CLUSTER - 1) / CLUSTER);
+  const int item0 = blockIdx.x / CLUSTER, item_step = gridDim.x / CLUSTER;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -171,66 +181,87 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kConvEpiWarps);
+      mbar_init(&tmem_empty[i], kConvEpiWarps * CLUSTER);  // pair mode: the peer's epilogue warps arrive remotely
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CLUSTER > 1) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * BLOCK_N;
-        const int mt = tile / p.n_tiles;
-        const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
-        const int b = mt / (p.tiles_w * p.tiles_h);
-        for (int t = 0; t < p.ntaps; ++t) {
-          const ConvTap tp = p.taps[t];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
-            tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
-            tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // ---------------- TMA producer: the whole warp walks the loop (converged), one elected lane issues
+    int stage = 0, phase = 0;
+    for (int item = item0; item < num_items; item += item_step) {
+      const int n0 = (item % p.n_tiles) * BLOCK_N;
+      const int mt = (item / p.n_tiles) * CLUSTER + crank;
+      const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
+      const int b = mt / (p.tiles_w * p.tiles_h);
+      for (int t = 0; t < p.ntaps; ++t) {
+        const ConvTap tp = p.taps[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (CLUSTER > 1) {
+              // the leader arms its barrier for the bytes of both CTAs; the peer's loads are credited to it as well
+              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + B_BYTES));
+              tma_load_4d_2sm(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+              tma_load_3d_2sm(sB + stage * B_BYTES, &p.tmBh, &full[stage], kc * kBlockK, tp.tap, n0 + crank * (BLOCK_N / 2));
+            } else {
+              mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
+              tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+              tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
+            }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ---------------- MMA issuer (pair mode: leader CTA only): converged warp, one elected lane issues.
+    // Shared-memory descriptors are built once per stage: inside the K loop only their start-address field advances.
+    if (crank == 0) {
+      const uint32_t idesc = p.idesc;
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA)), b_desc0 = umma_desc_sw128(smem_u32(sB));
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+          if (elect_one()) {
+            // descriptor start address is in 16-byte units: stage offsets and the 32-byte K step are plain adds
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * kABytes) >> 4);
+            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
-                     (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (CLUSTER > 1) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs of the pair) when the MMAs above have read it
+            if (CLUSTER > 1) umma_commit_2sm_mc(&empty[stage], static_cast<uint16_t>(0x3));
+            else umma_commit(&empty[stage]);
+            if (it == kiters - 1) {  // accumulator complete (in both CTAs' tensor memory)
+              if (CLUSTER > 1) umma_commit_2sm_mc(&tmem_full[acc], static_cast<uint16_t>(0x3));
+              else umma_commit(&tmem_full[acc]);
+            }
           }
-          umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused math -> NHWC global
     // kConvEpiWarps warps: warp w owns TMEM lane quadrant (w & 3) and the 32-column chunks ci with ci % 4 == (w-2)/4,
@@ -240,13 +271,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     const int row = q * 32 + lane;
     const int wi = row % p.tile_w, hi = row / p.tile_w;
     int acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n0 = (tile % p.n_tiles) * BLOCK_N;
-      const int mt = tile / p.n_tiles;
+    for (int item = item0; item < num_items; item += item_step) {
+      const int n0 = (item % p.n_tiles) * BLOCK_N;
+      const int mt = (item / p.n_tiles) * CLUSTER + crank;
       const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
       const int b = mt / (p.tiles_w * p.tiles_h);
       const int ow = ow0 + wi, oh = oh0 + hi;
-      const bool valid = (ow < p.Wo) && (oh < p.Ho);
+      const bool valid = (ow < p.Wo) && (oh < p.Ho) && (mt < p.m_tiles);  // mt >= m_tiles: padding tile of an odd pair
       const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
       const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
       if (C_BLOCKS > 0 && p.tma_store) {
@@ -275,7 +306,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           if (last_round) {  // this warp's last read of the accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
           }
           const int cbase = n0 + c0;
           const int ncols = min(32, limit - c0);  // multiple of 8
@@ -283,11 +317,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           switch (p.act) {
-            case UC_ACT_GELU: epi_math<UC_ACT_GELU>(f, p, cbase, ncols, valid, b, lane); break;
-            case UC_ACT_RELU: epi_math<UC_ACT_RELU>(f, p, cbase, ncols, valid, b, lane); break;
-            case UC_ACT_SILU: epi_math<UC_ACT_SILU>(f, p, cbase, ncols, valid, b, lane); break;
-            case UC_ACT_SIGMOID: epi_math<UC_ACT_SIGMOID>(f, p, cbase, ncols, valid, b, lane); break;
-            default: epi_math<UC_ACT_NONE>(f, p, cbase, ncols, valid, b, lane); break;
+            case UC_ACT_GELU: epi_math<UC_ACT_GELU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
+            case UC_ACT_RELU: epi_math<UC_ACT_RELU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
+            case UC_ACT_SILU: epi_math<UC_ACT_SILU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
+            case UC_ACT_SIGMOID: epi_math<UC_ACT_SIGMOID>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
+            default: epi_math<UC_ACT_NONE>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
           }
           if (valid) {
             if (p.res) {
@@ -345,7 +379,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           // nothing to read in the last round (narrow or edge tile): still release the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         if (C_BLOCKS > 0 && p.tma_store && r0 < limit) {  // uniform over the epilogue warps
           fence_proxy_async();
@@ -366,33 +403,48 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers / write its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CLUSTER > 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------- host side
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CLUSTER>
 static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
   constexpr int c_blocks = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + c_blocks * kABytes + 1024 + 256;
+  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + c_blocks * kABytes + 1024 + 256;
   static int per_sm = 0;
+  auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>;
   if (!per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_gemm_kernel<BLOCK_N, STAGES>, kConvThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kConvThreads, smem);
     if (e != cudaSuccess || n < 1) return set_error(UC_EINVAL, "conv_gemm<%d,%d>: does not fit on an SM", BLOCK_N, STAGES);
     constexpr int acc_cols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
     per_sm = std::min(n, 512 / (2 * acc_cols));  // TMEM: 512 columns per SM
   }
-  const int tiles = p.n_tiles * p.m_tiles;
-  const int grid = std::min(tiles, num_sms() * per_sm);
-  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d> launch: %s", BLOCK_N, STAGES, cudaGetErrorString(e));
+  const int items = p.n_tiles * ((p.m_tiles + CLUSTER - 1) / CLUSTER);
+  int grid = std::min(items * CLUSTER, num_sms() * per_sm);
+  grid -= grid % CLUSTER;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d,%d> launch: %s", BLOCK_N, STAGES, CLUSTER, cudaGetErrorString(e));
   return UC_OK;
 }
 
@@ -500,7 +552,9 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.kchunks = (d->Cin + kBlockK - 1) / kBlockK;
 
   const int gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 0;
-  const int bn = d->block_n == 129 ? 128 : d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
+  // block_n >= 1000 selects the cta_group::2 pair variant (1128 / 1192 / 1256)
+  const bool cluster2 = d->block_n >= 1000;
+  const int bn = cluster2 ? d->block_n - 1000 : d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
   if (bn == 0) return set_error(UC_EINVAL, "uc_conv2d: no N tile compatible with GroupNorm group size %d", gn_gs);
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(nt), static_cast<uint64_t>(d->Cout)};
@@ -530,15 +584,28 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
     return set_error(UC_EINVAL, "uc_conv2d: N tile %d incompatible with GroupNorm group size %d", bn, p.gn_gs);
   p.n_tiles = (d->Cout + bn - 1) / bn;
   p.m_tiles = m_tiles;
-  switch (d->block_n == 129 ? 129 : bn) {
-    case 256: return launch_conv<256, 3>(p, stream);
-    case 192: return launch_conv<192, 4>(p, stream);
-    case 128: return launch_conv<128, 5>(p, stream);
-    case 129: return launch_conv<128, 2>(p, stream);  // two CTAs per SM (benchmarking aid)
-    case 96: return launch_conv<96, 3>(p, stream);
-    case 64: return launch_conv<64, 3>(p, stream);
-    case 32: return launch_conv<32, 4>(p, stream);
-    case 16: return launch_conv<16, 4>(p, stream);
+  if (cluster2) {
+    uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(nt), static_cast<uint64_t>(d->Cout)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d->Cin) * es, static_cast<uint64_t>(nt) * d->Cin * es};
+    uint32_t box[3] = {static_cast<uint32_t>(kBlockK), 1, static_cast<uint32_t>(bn / 2)};
+    rc = encode_tmap(&p.tmBh, dt, 3, d->w, dims, strides, box);
+    if (rc) return rc;
+    p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, 2 * kBlockM, static_cast<uint32_t>(bn));  // UMMA M = 256
+    switch (bn) {
+      case 256: return launch_conv<256, 4, 2>(p, stream);  // 4 x 32 KB ring + 64 KB staging
+      case 192: return launch_conv<192, 5, 2>(p, stream);  // 5 x 28 KB + 48 KB
+      case 128: return launch_conv<128, 6, 2>(p, stream);  // 6 x 24 KB + 32 KB
+      default: return set_error(UC_EINVAL, "uc_conv2d: the cta_group::2 variant exists for block_n 128/192/256 only");
+    }
+  }
+  switch (bn) {
+    case 256: return launch_conv<256, 3, 1>(p, stream);
+    case 192: return launch_conv<192, 4, 1>(p, stream);
+    case 128: return launch_conv<128, 5, 1>(p, stream);
+    case 96: return launch_conv<96, 3, 1>(p, stream);
+    case 64: return launch_conv<64, 3, 1>(p, stream);
+    case 32: return launch_conv<32, 4, 1>(p, stream);
+    case 16: return launch_conv<16, 4, 1>(p, stream);
     default: return set_error(UC_EINVAL, "uc_conv2d: unsupported block_n %d", bn);
   }
 }

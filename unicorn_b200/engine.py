@@ -166,6 +166,7 @@ class UnicornEngine:
     def _tune(self, x, w, k, stride, pad, out, kw, Cout, gn):
         gs = Cout // gn if gn else 0
         cands = [0] + [b for b in (64, 96, 128, 192, 256) if (not gs or b % gs == 0) and b < 2 * Cout + 64]
+        cands += [1000 + b for b in (128, 192, 256) if b in cands]  # 2-CTA cluster variants with weight multicast
         scratch = torch.empty_like(out)
         kw2 = dict(kw)
         if gn:
