@@ -20,6 +20,8 @@ constexpr int kCorrC = 128;      // embedding channels
 constexpr int kCorrTile = 128;   // current positions per CTA == reference positions per chunk
 constexpr int kCorrStages = 4;
 constexpr int kCorrTileBytes = kCorrTile * kCorrC * 2;  // 32 KB (two 128B-swizzled 64-channel halves)
+constexpr int kCorrSoftmaxWarps = 16;                  // 4 per TMEM lane quadrant, each owning 32 of the 128 chunk columns
+constexpr int kCorrThreads = (2 + kCorrSoftmaxWarps) * 32;
 
 struct alignas(64) CorrParams {
   CUtensorMap tmQ, tmK;
@@ -36,7 +38,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int NOBJ>
-__global__ void __launch_bounds__(192, 1) corr_kernel(const __grid_constant__ CorrParams p) {
+__global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_constant__ CorrParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(192, 1) corr_kernel(const __grid_constant__ Co
     prefetch_tmap(&p.tmK);
     mbar_init(q_full, 1);
     for (int i = 0; i < kCorrStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kCorrSoftmaxWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -71,49 +73,59 @@ __global__ void __launch_bounds__(192, 1) corr_kernel(const __grid_constant__ Co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: converged warp, one elected lane issues (keeps addresses in uniform registers)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kCorrTileBytes);
       tma_load_2d(sQ, &p.tmQ, q_full, 0, j0);
       tma_load_2d(sQ + kCorrTileBytes / 2, &p.tmQ, q_full, 64, j0);
-      int stage = 0, phase = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0, phase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&k_empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[stage], kCorrTileBytes);
         uint8_t* dst = sK + stage * kCorrTileBytes;
         tma_load_2d(dst, &p.tmK, &k_full[stage], 0, c * kCorrTile);
         tma_load_2d(dst + kCorrTileBytes / 2, &p.tmK, &k_full[stage], 64, c * kCorrTile);
-        if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(q_full, 0);
-      const uint32_t q_addr = smem_u32(sQ);
-      int stage = 0, phase = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        mbar_wait(&s_empty[buf], ((c >> 1) & 1) ^ 1);
-        mbar_wait(&k_full[stage], phase);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + stage * kCorrTileBytes);
+    // MMA issuer: converged warp, one elected lane issues; descriptors built once, only the address field advances
+    mbar_wait(q_full, 0);
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ)), k_desc0 = umma_desc_sw128(smem_u32(sK));
+    const uint32_t idesc = p.idesc;
+    int stage = 0, phase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&s_empty[buf], ((c >> 1) & 1) ^ 1);
+      mbar_wait(&k_full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t k_desc = k_desc0 + static_cast<uint64_t>((stage * kCorrTileBytes) >> 4);
 #pragma unroll
         for (int ks = 0; ks < kCorrC / 16; ++ks) {
-          const uint32_t o = (ks >> 2) * (kCorrTileBytes / 2) + (ks & 3) * 32;
-          umma_f16(tmem_base + buf * kCorrTile, umma_desc_sw128(q_addr + o), umma_desc_sw128(k_addr + o), p.idesc,
-                   ks != 0 ? 1u : 0u);
+          const uint64_t o = static_cast<uint64_t>(((ks >> 2) * (kCorrTileBytes / 2) + (ks & 3) * 32) >> 4);
+          umma_f16(tmem_base + buf * kCorrTile, q_desc + o, k_desc + o, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[stage]);
         umma_commit(&s_full[buf]);
-        if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
     }
-    __syncwarp();
   } else {
-    // ---------------- online softmax + label propagation; thread <-> current position
+    // ---------------- online softmax + label propagation
+    // 16 warps: warp w owns TMEM lane quadrant (w & 3) (= 32 current positions) and columns [32*cg, 32*cg+32) of every
+    // 128-column similarity chunk, cg = (w-2)/4.  Each thread keeps a private running (max, sum, weighted label sums)
+    // for its (position, column group); the four partial states of a position are merged once at the end.  Four warps
+    // per scheduler hide the tcgen05.ld / MUFU latencies that a single warp per scheduler could not.
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int tid = (warp - 2) * 32 + lane;  // 0..127 among the softmax threads
+    const int tid = threadIdx.x - 64;  // 0..511 among the softmax threads
     const int j = j0 + row;
     constexpr float kLog2e = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
@@ -124,64 +136,83 @@ __global__ void __launch_bounds__(192, 1) corr_kernel(const __grid_constant__ Co
       const int buf = c & 1;
       const int i0 = c * kCorrTile;
       float* vb = sV + buf * NOBJ * kCorrTile;
+      if (tid < kCorrTile) {
 #pragma unroll
-      for (int o = 0; o < NOBJ; ++o) {
-        float v = 0.f;
-        if (o < p.n_obj && i0 + tid < p.n_ref) v = __ldg(p.V + static_cast<long>(o) * p.ldv + i0 + tid);
-        vb[o * kCorrTile + tid] = v;
+        for (int o = 0; o < NOBJ; ++o) {
+          float v = 0.f;
+          if (o < p.n_obj && i0 + tid < p.n_ref) v = __ldg(p.V + static_cast<long>(o) * p.ldv + i0 + tid);
+          vb[o * kCorrTile + tid] = v;
+        }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kCorrSoftmaxWarps * 32) : "memory");
       mbar_wait(&s_full[buf], (c >> 1) & 1);
       tc_fence_after();
       const int nvalid = min(kCorrTile, p.n_ref - i0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < kCorrTile; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrTile + c0, v);
-        tmem_ld_wait();
-        if (c0 == kCorrTile - 32) {
-          // all of this thread's reads of the S buffer are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[buf]);
-        }
-        if (c0 >= nvalid) continue;  // warp-uniform: fully masked group of the tail chunk
-        float s[32];
-        float cmax = -INFINITY;
+      const int c0 = cg * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrTile + c0, v);
+      tmem_ld_wait();
+      // this warp's only read of the S buffer is done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[buf]);
+      if (c0 >= nvalid) continue;  // warp-uniform: fully masked column group of the tail chunk
+      float s[32];
+      float cmax = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) s[t] = __uint_as_float(v[t]) * kLog2e;
-        if (nvalid < kCorrTile) {  // tail chunk only (warp-uniform)
+      for (int t = 0; t < 32; ++t) s[t] = __uint_as_float(v[t]) * kLog2e;
+      if (nvalid < kCorrTile) {  // tail chunk only (warp-uniform)
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (c0 + t >= nvalid) s[t] = -INFINITY;
-        }
+        for (int t = 0; t < 32; ++t)
+          if (c0 + t >= nvalid) s[t] = -INFINITY;
+      }
 #pragma unroll
-        for (int t = 0; t < 32; ++t) cmax = fmaxf(cmax, s[t]);
-        const float m_new = fmaxf(m, cmax);
-        const float scale = fast_exp2(m - m_new);
-        m = m_new;
-        l *= scale;
+      for (int t = 0; t < 32; ++t) cmax = fmaxf(cmax, s[t]);
+      const float m_new = fmaxf(m, cmax);
+      const float scale = fast_exp2(m - m_new);
+      m = m_new;
+      l *= scale;
 #pragma unroll
-        for (int o = 0; o < NOBJ; ++o) acc[o] *= scale;
+      for (int o = 0; o < NOBJ; ++o) acc[o] *= scale;
 #pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          float pr[4];
+      for (int t = 0; t < 32; t += 4) {
+        float pr[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { pr[u] = fast_exp2(s[t + u] - m_new); l += pr[u]; }
+        for (int u = 0; u < 4; ++u) { pr[u] = fast_exp2(s[t + u] - m_new); l += pr[u]; }
 #pragma unroll
-          for (int o = 0; o < NOBJ; ++o) {
-            const float4 vv = *reinterpret_cast<const float4*>(vb + o * kCorrTile + c0 + t);
-            acc[o] = fmaf(pr[0], vv.x, acc[o]); acc[o] = fmaf(pr[1], vv.y, acc[o]);
-            acc[o] = fmaf(pr[2], vv.z, acc[o]); acc[o] = fmaf(pr[3], vv.w, acc[o]);
-          }
+        for (int o = 0; o < NOBJ; ++o) {
+          const float4 vv = *reinterpret_cast<const float4*>(vb + o * kCorrTile + c0 + t);
+          acc[o] = fmaf(pr[0], vv.x, acc[o]); acc[o] = fmaf(pr[1], vv.y, acc[o]);
+          acc[o] = fmaf(pr[2], vv.z, acc[o]); acc[o] = fmaf(pr[3], vv.w, acc[o]);
         }
       }
     }
-    if (j < p.n_cur) {
-      const float inv = 1.f / l;
+    // merge the four column groups of every position (the K ring is idle now: reuse it as scratch)
+    float* part = reinterpret_cast<float*>(sK);  // [4][128][2 + NOBJ]
+    float* mine = part + (cg * kCorrTile + row) * (2 + NOBJ);
+    mine[0] = m; mine[1] = l;
+#pragma unroll
+    for (int o = 0; o < NOBJ; ++o) mine[2 + o] = acc[o];
+    asm volatile("bar.sync 1, %0;" ::"n"(kCorrSoftmaxWarps * 32) : "memory");
+    if (cg == 0 && j < p.n_cur) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) M = fmaxf(M, part[(g * kCorrTile + row) * (2 + NOBJ)]);
+      float L = 0.f, A[NOBJ];
+#pragma unroll
+      for (int o = 0; o < NOBJ; ++o) A[o] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float* pg = part + (g * kCorrTile + row) * (2 + NOBJ);
+        const float w = fast_exp2(pg[0] - M);  // a group that saw only masked columns has m = -inf -> weight 0
+        L = fmaf(pg[1], w, L);
+#pragma unroll
+        for (int o = 0; o < NOBJ; ++o) A[o] = fmaf(pg[2 + o], w, A[o]);
+      }
+      const float inv = 1.f / L;
 #pragma unroll
       for (int o = 0; o < NOBJ; ++o)
-        if (o < p.n_obj) p.out[static_cast<long>(o) * p.ldo + j] = acc[o] * inv;
+        if (o < p.n_obj) p.out[static_cast<long>(o) * p.ldo + j] = A[o] * inv;
     }
   }
   tc_fence_before();
@@ -201,7 +232,7 @@ static int launch_corr(const CorrParams& p, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "corr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  corr_kernel<NOBJ><<<grid, 192, smem, stream>>>(p);
+  corr_kernel<NOBJ><<<grid, kCorrThreads, smem, stream>>>(p);
   return check_launch("uc_corr_propagate");
 }
 
