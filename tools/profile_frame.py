@@ -3,7 +3,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from unicorn_b200 import _lib
+from unicorn_b200 import _lib, ops
 from unicorn_b200.engine import UnicornEngine
 from unicorn_b200.sot import UnicornSOTTrack
 from unicorn_b200.synthetic import make_video
@@ -19,8 +19,12 @@ trk.initialize_tensor(frames[0:1], boxes[0, 0])
 print("launches after init", _lib.LAUNCHES)
 for i in range(nfr):
     l0 = _lib.LAUNCHES
+    ops.CONV_TRACE = [] if i == nfr - 1 else None
     trk.track_tensor(frames[1 + i:2 + i])
     print("frame", i, "launches", _lib.LAUNCHES - l0)
+if os.environ.get("UC_CONV_TRACE"):
+    import json
+    json.dump(ops.CONV_TRACE, open(os.environ["UC_CONV_TRACE"], "w"))
 if len(sys.argv) > 3:
     eng.save_tuning(sys.argv[3])
     print("saved tuning table", sys.argv[3], len(eng._bn_cache))

@@ -6,11 +6,11 @@
 // the NHWC output map; for every filter tap the TMA engine fetches the shifted tile_w x tile_h x 64-channel
 // box of the input straight into 128B-swizzled shared memory (out-of-bounds coordinates are zero-filled by
 // the hardware, which is the convolution's zero padding), so no im2col buffer ever exists.  A single elected
-// thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16/fp16 in, fp32 accumulate in TMEM); four epilogue
-// warps read the accumulator back with tcgen05.ld and apply bias / activation / layer-scale+residual, and
-// optionally accumulate GroupNorm statistics, before a vectorised NHWC store.
+// thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16/fp16 in, fp32 accumulate in a double-buffered TMEM
+// accumulator); sixteen epilogue warps read the accumulator back with tcgen05.ld and apply bias / activation /
+// layer-scale+residual, and optionally accumulate GroupNorm statistics, before 256-bit (one L2 sector per lane) stores.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue.
 // Reference call sites replaced: see include/unicorn_b200.h (uc_conv2d).
 #include <algorithm>
 #include "uc_ptx.cuh"
@@ -34,7 +34,6 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   CUtensorMap tmBh;  // half-height weight box for the 2-CTA multicast variant
-  CUtensorMap tmC;  // output map for the TMA store (16-bit outputs)
   ConvTap taps[kMaxTaps];
   int ntaps, kchunks;
   int n_tiles, m_tiles;
@@ -46,7 +45,8 @@ struct alignas(64) ConvKernelParams {
   const void* res;
   int ldres;
   void* y;
-  int ldy, y_dtype, act, tma_store;
+  int ldy, y_dtype, act;
+  int wide_store, wide_res;  // 256-bit stores / residual loads possible (32-byte aligned rows)
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -56,86 +56,79 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exact-erf GELU (nn.GELU()) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below the bf16 output ulp):
-// two MUFU ops (rcp, ex2) and ~12 FMAs instead of libdevice erff's long dependent chain — the epilogue warps have
-// nobody to hide latency behind.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = fast_ex2(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly, e, 1.f);
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot per two elements
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
 }
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact (erf) GELU, nn.GELU(), as x * sigmoid(x * P(x^2)): P is the degree-4 least-squares fit of logit(Phi(x)) / x,
+// max |error| 3.3e-6 over the whole real line (tools/fit_gelu.py; the bf16 output ulp is >= 1.5e-5 wherever |y| > 4e-3,
+// and the fit saturates correctly: y -> x for x -> +inf, y -> -0 for x -> -inf).  Per PAIR of elements: 8 packed
+// FMA-pipe instructions + 2 x (ex2, rcp) — the earlier Abramowitz-Stegun form cost ~25 issue slots per element and the
+// epilogue, not the tensor pipe, set the pace of every pwconv1 (ncu: profiles/r1_ncu_conv_epilogue.md).
+__device__ __forceinline__ f32x2 gelu2(f32x2 x) {
+  // coefficients pre-multiplied by -log2(e): e = 2^(x * P'(x^2)) = exp(-q(x))
+  const f32x2 c0 = pk2(-2.30204844f, -2.30204844f), c1 = pk2(-0.105217814f, -0.105217814f), c2 = pk2(3.54831049e-4f, 3.54831049e-4f),
+              c3 = pk2(8.93110919e-5f, 8.93110919e-5f), c4 = pk2(-3.29185241e-6f, -3.29185241e-6f), one = pk2(1.f, 1.f);
+  const f32x2 t = mul2(x, x);
+  f32x2 pz = fma2(c4, t, c3);
+  pz = fma2(pz, t, c2);
+  pz = fma2(pz, t, c1);
+  pz = fma2(pz, t, c0);
+  const f32x2 u = mul2(x, pz);
+  const f32x2 d = add2(pk2(fast_ex2(lo2(u)), fast_ex2(hi2(u))), one);
+  return mul2(x, pk2(fast_rcp(lo2(d)), fast_rcp(hi2(d))));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return lo2(gelu2(pk2(x, x))); }
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case UC_ACT_RELU: return fmaxf(x, 0.f);
     case UC_ACT_GELU: return gelu_erf(x);
-    case UC_ACT_SILU: return __fdividef(x, 1.f + fast_ex2(-x * 1.4426950408889634f));
-    case UC_ACT_SIGMOID: return __fdividef(1.f, 1.f + fast_ex2(-x * 1.4426950408889634f));
+    case UC_ACT_SILU: return x * fast_rcp(1.f + fast_ex2(-x * 1.4426950408889634f));
+    case UC_ACT_SIGMOID: return fast_rcp(1.f + fast_ex2(-x * 1.4426950408889634f));
     default: return x;
   }
 }
+__device__ __forceinline__ uint32_t pack2_fast(float lo, float hi, bool f16) {  // one F2FP per pair
+  if (f16) { const __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<const uint32_t*>(&h); }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
-// Epilogue of one 32-column chunk of one tile, specialised on the activation so that the inner loops are branch-free.
-template <int ACT>
-__device__ __forceinline__ void epi_math(float (&f)[32], const ConvKernelParams& p, int cbase, int ncols, bool valid, int b,
-                                         int lane, bool tile_ok) {
-  if (p.bias) {
+// GroupNorm partial sums of one epilogue item (this warp's 32 rows x ncols columns starting at channel cbase).  A group
+// may straddle items / warps / CTAs: partial sums are simply added by the order-independent fixed-point atomics.
+__device__ __forceinline__ void gn_partial_sums(const float (&f)[16], const ConvKernelParams& p, int cbase, int ncols, bool valid,
+                                             int b, int lane, bool tile_ok) {
+  int c = 0;
+#pragma unroll 1
+  while (c < ncols) {
+    const int g = (cbase + c) / p.gn_gs;
+    const int end = min(ncols, (g + 1) * p.gn_gs - cbase);
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-      }
+    for (int j = 0; j < 16; ++j) {
+      const float x = (valid && j >= c && j < end) ? f[j] : 0.f;
+      s1 += x;
+      s2 = fmaf(x, x, s2);
     }
-  }
-  if (p.gn_stats) {
-    // per-group partial sums of this warp's 32 rows x chunk columns; a group may span several chunks — partial sums
-    // are simply added by the (order-independent) integer atomics.
-    float gs_sum = 0.f, gs_sq = 0.f;
-    int gs_left = p.gn_gs - (cbase % p.gn_gs);
-    int gs_group = cbase / p.gn_gs;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < ncols) {
-        const float x = valid ? f[j] : 0.f;
-        gs_sum += x;
-        gs_sq += x * x;
-        if (--gs_left == 0 || j == ncols - 1) {
-          float s1 = gs_sum, s2 = gs_sq;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          }
-          if (lane == 0 && tile_ok) {
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + gs_group) * 2;
-            atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
-            atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
-          }
-          gs_sum = 0.f; gs_sq = 0.f;
-          if (gs_left == 0) { gs_left = p.gn_gs; ++gs_group; }
-        }
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-  }
-  if (ACT != UC_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ACT);
-  }
-  if (p.gamma) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
-        f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
-      }
+    if (lane == 0 && tile_ok) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + g) * 2;
+      atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+      atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
     }
+    c = end;
   }
 }
 
@@ -153,13 +146,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   constexpr int B_BYTES = (BLOCK_N / CLUSTER) * kBlockK * 2;  // per-CTA weight bytes per stage
   constexpr uint32_t ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
-  constexpr int C_BLOCKS = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;  // 64-channel staging blocks for the TMA store
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kABytes;
-  uint8_t* sC = sB + STAGES * B_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + C_BLOCKS * kABytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
@@ -264,12 +255,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused math -> NHWC global
-    // kConvEpiWarps warps: warp w owns TMEM lane quadrant (w & 3) and the 32-column chunks ci with ci % 4 == (w-2)/4,
-    // so four warps share each scheduler and hide each other's latencies.
+    // 16 warps = 4 TMEM lane quadrants (q = warp % 4, fixed by the hardware) x 4 column groups (cg).  Work item = 32 rows x 16
+    // channels: warp (q, cg) owns rows 32q..32q+31 and the channels 64 rd + 16 cg of round rd, so the warps are balanced for
+    // every N tile.  A lane holds 16 consecutive channels of one pixel = 32 bytes of bf16 = exactly one L2 sector, written
+    // with ONE 256-bit store (no partial sectors, no staging buffer, no barrier): the warps are completely independent and
+    // drift apart, which is what hides the TMEM / L2 / MUFU latencies of one another.
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int wi = row % p.tile_w, hi = row / p.tile_w;
+    const bool f16 = p.y_dtype == UC_F16;
+    constexpr int ROUNDS = (BLOCK_N + 63) / 64;
     int acc = 0, acc_phase = 0;
     for (int item = item0; item < num_items; item += item_step) {
       const int n0 = (item % p.n_tiles) * BLOCK_N;
@@ -277,106 +273,47 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
       const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
       const int b = mt / (p.tiles_w * p.tiles_h);
       const int ow = ow0 + wi, oh = oh0 + hi;
-      const bool valid = (ow < p.Wo) && (oh < p.Ho) && (mt < p.m_tiles);  // mt >= m_tiles: padding tile of an odd pair
+      const bool tile_ok = mt < p.m_tiles;  // false: padding tile of an odd pair
+      const bool valid = (ow < p.Wo) && (oh < p.Ho) && tile_ok;
       const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
       const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
-      if (C_BLOCKS > 0 && p.tma_store) {
-        // the staging blocks are about to be overwritten: the previous tile's TMA stores must have read them
-        if (lane == 0 && q == 0 && cg < 2) tma_store_wait_read();  // the two issuing threads (warps 4 and 8)
-        asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
-      }
+      // this warp's last round with columns to read: the accumulator is handed back to the MMA warp right after it
+      const int last_rd = (limit - 1 - cg * 16) >= 0 ? min(ROUNDS - 1, (limit - 1 - cg * 16) / 64) : -1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int r0 = 0; r0 < BLOCK_N; r0 += 128) {
-        const int c0 = r0 + cg * 32;
-        const bool last_round = (r0 + 128 >= BLOCK_N);
-        if (c0 < limit && c0 < BLOCK_N) {
-          uint32_t v[32];
-          if constexpr (BLOCK_N % 32 == 0) {
-            tmem_ld_32x32(t_acc + c0, v);
+      for (int rd = 0; rd <= last_rd; ++rd) {
+        const int c0 = rd * 64 + cg * 16;
+        const int cbase = n0 + c0;
+        const int ncols = min(16, limit - c0);  // 8 or 16
+        uint32_t v[16];
+        tmem_ld_32x16(t_acc + c0, v);
+        float4 bb[4];
+        if (p.bias) {  // in flight together with the TMEM load
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = (4 * j < ncols) ? __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t rw[8];
+        const bool has_res = p.res && valid;
+        if (has_res) {  // residual: the same 32-byte sector of the shortcut tensor
+          const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
+          if (p.wide_res && ncols == 16) {
+            ldg_v8(r, rw);
           } else {
-            uint32_t h[16];
-            tmem_ld_32x16(t_acc + c0, h);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
-          }
-          tmem_ld_wait();
-          if (last_round) {  // this warp's last read of the accumulator: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
-              else mbar_arrive(&tmem_empty[acc]);
+            for (int j = 0; j < 2; ++j) {
+              uint4 rv = make_uint4(0, 0, 0, 0);
+              if (8 * j < ncols) rv = __ldg(reinterpret_cast<const uint4*>(r) + j);
+              rw[4 * j] = rv.x; rw[4 * j + 1] = rv.y; rw[4 * j + 2] = rv.z; rw[4 * j + 3] = rv.w;
             }
           }
-          const int cbase = n0 + c0;
-          const int ncols = min(32, limit - c0);  // multiple of 8
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          switch (p.act) {
-            case UC_ACT_GELU: epi_math<UC_ACT_GELU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
-            case UC_ACT_RELU: epi_math<UC_ACT_RELU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
-            case UC_ACT_SILU: epi_math<UC_ACT_SILU>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
-            case UC_ACT_SIGMOID: epi_math<UC_ACT_SIGMOID>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
-            default: epi_math<UC_ACT_NONE>(f, p, cbase, ncols, valid, b, lane, mt < p.m_tiles); break;
-          }
-          if (valid) {
-            if (p.res) {
-              const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldres + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + j));
-                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    f[j + 2 * t] += bits16_to_float(rw[t] & 0xffffu, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
-                    f[j + 2 * t + 1] += bits16_to_float(rw[t] >> 16, p.y_dtype == UC_F16 ? UC_F16 : UC_BF16);
-                  }
-                }
-              }
-            }
-            if (p.y_dtype == UC_F32) {
-              float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              }
-            } else if (!p.tma_store) {
-              uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  uint4 o;
-                  o.x = pack2_16(f[j], f[j + 1], p.y_dtype);
-                  o.y = pack2_16(f[j + 2], f[j + 3], p.y_dtype);
-                  o.z = pack2_16(f[j + 4], f[j + 5], p.y_dtype);
-                  o.w = pack2_16(f[j + 6], f[j + 7], p.y_dtype);
-                  *reinterpret_cast<uint4*>(yp + j) = o;
-                }
-              }
-            }
-          }
-          if (C_BLOCKS > 0 && p.tma_store) {
-            // Stage in shared memory in the 128B-swizzled layout of a TMA box (64 channels per block); the TMA engine
-            // then writes full lines and clips the out-of-range rows / channels of edge tiles.
-            uint8_t* blk = sC + (c0 >> 6) * kABytes;
-            const int kb = (c0 & 32) >> 3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack2_16(f[8 * j], f[8 * j + 1], p.y_dtype);
-              o.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.y_dtype);
-              o.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.y_dtype);
-              o.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.y_dtype);
-              *reinterpret_cast<uint4*>(blk + row * 128 + (((kb + j) ^ (row & 7)) << 4)) = o;
-            }
-          }
-        } else if (last_round) {
-          // nothing to read in the last round (narrow or edge tile): still release the accumulator
+        }
+        tmem_ld_wait();
+        if (rd == last_rd) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -384,22 +321,94 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
             else mbar_arrive(&tmem_empty[acc]);
           }
         }
-        if (C_BLOCKS > 0 && p.tma_store && r0 < limit) {  // uniform over the epilogue warps
-          fence_proxy_async();
-          asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
-          if (lane == 0 && q == 0 && cg < 2) {  // two issuing threads: warps 4 (block r0/64) and 8 (block r0/64 + 1)
-            const int blk = (r0 >> 6) + cg;
-            if (blk * 64 < limit) {
-              tma_store_4d(&p.tmC, sC + blk * kABytes, n0 + blk * 64, ow0, oh0, b);
-              tma_store_commit();
+        f32x2 h[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb[j].x, bb[j].y));
+          h[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb[j].z, bb[j].w));
+        }
+        if (p.act == UC_ACT_GELU && !p.gn_stats) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = gelu2(h[j]);
+        } else if (p.gn_stats || p.act != UC_ACT_NONE) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[2 * j] = lo2(h[j]); f[2 * j + 1] = hi2(h[j]); }
+          if (p.gn_stats) gn_partial_sums(f, p, cbase, ncols, valid, b, lane, tile_ok);
+          switch (p.act) {
+            case UC_ACT_RELU:
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              break;
+            case UC_ACT_NONE: break;
+            default:
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
+              break;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = pk2(f[2 * j], f[2 * j + 1]);
+        }
+        if (p.gamma) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * j < ncols) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase) + j);
+              h[2 * j] = mul2(h[2 * j], pk2(g.x, g.y));
+              h[2 * j + 1] = mul2(h[2 * j + 1], pk2(g.z, g.w));
             }
           }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const f32x2 rr = f16 ? pk2(bits16_to_float(rw[t] & 0xffffu, UC_F16), bits16_to_float(rw[t] >> 16, UC_F16))
+                                 : pk2(bf16lo(rw[t]), bf16hi(rw[t]));
+            h[t] = add2(h[t], rr);
+          }
+        }
+        if (valid) {
+          if (p.y_dtype == UC_F32) {
+            float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + cbase;
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[2 * j] = __float_as_uint(lo2(h[j])); o[2 * j + 1] = __float_as_uint(hi2(h[j])); }
+            if (p.wide_store) {
+              stg_v8(yp, o);
+              if (ncols == 16) stg_v8(yp + 8, o + 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (4 * j < ncols) *(reinterpret_cast<uint4*>(yp) + j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
+            }
+          } else {
+            uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + cbase;
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = pack2_fast(lo2(h[j]), hi2(h[j]), f16);
+            if (p.wide_store && ncols == 16) {
+              stg_v8(yp, o);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                if (8 * j < ncols) *(reinterpret_cast<uint4*>(yp) + j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+      if (last_rd < 0) {  // narrow or edge tile: nothing to read for this warp, still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (C_BLOCKS > 0 && p.tma_store && lane == 0 && q == 0 && cg < 2) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -415,8 +424,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 
 template <int BLOCK_N, int STAGES, int CLUSTER>
 static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
-  constexpr int c_blocks = (BLOCK_N % 64 == 0) ? BLOCK_N / 64 : 0;
-  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + c_blocks * kABytes + 1024 + 256;
+  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256;
   static int per_sm = 0;
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>;
   if (!per_sm) {
@@ -563,16 +571,10 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
     rc = encode_tmap(&p.tmB, dt, 3, d->w, dims, strides, box);
     if (rc) return rc;
   }
-  p.tma_store = 0;
-  if (d->y_dtype != UC_F32 && (bn % 64) == 0) {  // every 64-channel store box must lie inside this CTA's N tile
-    const CUtensorMapDataType dty = d->y_dtype == UC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho), static_cast<uint64_t>(B)};
-    uint64_t strides[3] = {static_cast<uint64_t>(d->ldy) * es, static_cast<uint64_t>(p.Wo) * d->ldy * es,
-                           static_cast<uint64_t>(p.Ho) * p.Wo * d->ldy * es};
-    uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
-    rc = encode_tmap(&p.tmC, dty, 4, d->y, dims, strides, box);
-    if (rc) return rc;
-    p.tma_store = 1;
+  {
+    const size_t yes = d->y_dtype == UC_F32 ? 4 : 2;
+    p.wide_store = ((d->ldy * yes) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->y) % 32 == 0);
+    p.wide_res = d->res && ((d->ldres * es) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->res) % 32 == 0);
   }
   p.Cout = d->Cout;
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
@@ -592,20 +594,20 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
     if (rc) return rc;
     p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, 2 * kBlockM, static_cast<uint32_t>(bn));  // UMMA M = 256
     switch (bn) {
-      case 256: return launch_conv<256, 4, 2>(p, stream);  // 4 x 32 KB ring + 64 KB staging
-      case 192: return launch_conv<192, 5, 2>(p, stream);  // 5 x 28 KB + 48 KB
-      case 128: return launch_conv<128, 6, 2>(p, stream);  // 6 x 24 KB + 32 KB
+      case 256: return launch_conv<256, 6, 2>(p, stream);  // 6 x 32 KB ring
+      case 192: return launch_conv<192, 7, 2>(p, stream);  // 7 x 28 KB
+      case 128: return launch_conv<128, 8, 2>(p, stream);  // 8 x 24 KB
       default: return set_error(UC_EINVAL, "uc_conv2d: the cta_group::2 variant exists for block_n 128/192/256 only");
     }
   }
   switch (bn) {
-    case 256: return launch_conv<256, 3, 1>(p, stream);
-    case 192: return launch_conv<192, 4, 1>(p, stream);
-    case 128: return launch_conv<128, 5, 1>(p, stream);
-    case 96: return launch_conv<96, 3, 1>(p, stream);
-    case 64: return launch_conv<64, 3, 1>(p, stream);
-    case 32: return launch_conv<32, 4, 1>(p, stream);
-    case 16: return launch_conv<16, 4, 1>(p, stream);
+    case 256: return launch_conv<256, 4, 1>(p, stream);
+    case 192: return launch_conv<192, 5, 1>(p, stream);
+    case 128: return launch_conv<128, 6, 1>(p, stream);
+    case 96: return launch_conv<96, 6, 1>(p, stream);
+    case 64: return launch_conv<64, 8, 1>(p, stream);
+    case 32: return launch_conv<32, 8, 1>(p, stream);
+    case 16: return launch_conv<16, 8, 1>(p, stream);
     default: return set_error(UC_EINVAL, "uc_conv2d: unsupported block_n %d", bn);
   }
 }

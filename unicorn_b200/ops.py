@@ -41,6 +41,9 @@ def pack_conv_weight(w, dtype=torch.bfloat16, cout_pad=8):
     return out.contiguous()
 
 
+CONV_TRACE = None
+
+
 def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=None, res=None, out=None,
            out_dtype=None, block_n=0, gn_stats=None, gn_groups=0):
     """x: NHWC view (B,H,W,Cin) bf16/f16.  w_packed: [Cout, KH*KW, Cin].  Returns NHWC (B,Ho,Wo,Cout)."""
@@ -69,6 +72,9 @@ def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=
     d.y, d.ldy, d.y_dtype = _p(out), _nhwc_ld(out), _DT[out.dtype]
     d.block_n = block_n
     d.gn_stats, d.gn_groups = _p(gn_stats), gn_groups
+    if CONV_TRACE is not None:  # tools/profile_frame.py: conv launches in issue order, to label an ncu launch list
+        CONV_TRACE.append(dict(M=B * Ho * Wo, N=Cout, K=Cin * KH * KW, k=KH, s=stride, bn=block_n, act=act, gn=gn_groups,
+                               f32=int(out.dtype == torch.float32)))
     _lib.check(_lib.lib().uc_conv2d(ctypes.byref(d), _lib.stream_ptr()), "uc_conv2d")
     return out
 
