@@ -12,6 +12,8 @@ namespace uc {
 __global__ void __launch_bounds__(256) sample_embed_kernel(const uint16_t* __restrict__ embed, int ld, int h, int w, int C, int dtype,
                                                             const float* __restrict__ boxes, int ldb, const int* __restrict__ count,
                                                             int n_max, float stride, float* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int n = count ? min(*count, n_max) : n_max;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(256) sample_embed_kernel(const uint16_t* __res
 // feats[i,j] = <E_i, M_j>; one block computes the whole matrix into global, then row / column softmax passes.
 __global__ void __launch_bounds__(256) feats_kernel(const float* __restrict__ E, const float* __restrict__ Mm, int N, int M, int C,
                                                      float* __restrict__ feats) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || j >= M) return;
   float acc = 0.f;
@@ -49,6 +53,8 @@ __global__ void __launch_bounds__(256) feats_kernel(const float* __restrict__ E,
 }
 __global__ void __launch_bounds__(128) softmax_stats_kernel(const float* __restrict__ feats, int N, int M, float* __restrict__ rmax,
                                                             float* __restrict__ rsum, float* __restrict__ cmax, float* __restrict__ csum) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   // blocks [0,N): row i ; blocks [N, N+M): column j
   __shared__ float red[128];
   const bool is_row = blockIdx.x < N;
@@ -73,6 +79,8 @@ __global__ void __launch_bounds__(256) bisoftmax_kernel(const float* __restrict_
                                                          const float* __restrict__ rsum, const float* __restrict__ cmax,
                                                          const float* __restrict__ csum, const float* __restrict__ lab_d,
                                                          const float* __restrict__ lab_m, float* __restrict__ scores) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long>(N) * M) return;
   const int i = static_cast<int>(t / M), j = static_cast<int>(t % M);
@@ -86,6 +94,8 @@ __global__ void __launch_bounds__(256) bisoftmax_kernel(const float* __restrict_
 // unicorn/tracker/matching.py:65-68)
 __global__ void __launch_bounds__(256) box_iou_kernel(const float* __restrict__ a, int lda, int N, const float* __restrict__ b, int ldb,
                                                        int M, float* __restrict__ out, float plus1) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long>(N) * M) return;
   const float* p = a + (t / M) * lda;
@@ -104,7 +114,7 @@ extern "C" int uc_sample_embed(const void* embed, int ld, int h, int w, int C, i
                                const int* count_dev, int n_max, float stride, float* out, void* stream_v) {
   if (!embed || !boxes || !out || n_max < 0 || h < 2 || w < 2 || ldb < 4) return set_error(UC_EINVAL, "uc_sample_embed: bad arguments");
   if (n_max == 0) return UC_OK;
-  sample_embed_kernel<<<(n_max + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(static_cast<const uint16_t*>(embed), ld, h, w, C, dtype,
+  launch_pdl(sample_embed_kernel, (n_max + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_v), static_cast<const uint16_t*>(embed), ld, h, w, C, dtype,
                                                                                         boxes, ldb, count_dev, n_max, stride, out);
   return check_launch("uc_sample_embed");
 }
@@ -118,15 +128,15 @@ extern "C" int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, i
   float* rsum = rmax + N;
   float* cmax = rsum + N;
   float* csum = cmax + M;
-  feats_kernel<<<dim3((M + 255) / 256, N), 256, 0, stream>>>(det_embeds, memo_embeds, N, M, C, feats);
-  softmax_stats_kernel<<<N + M, 128, 0, stream>>>(feats, N, M, rmax, rsum, cmax, csum);
-  bisoftmax_kernel<<<static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, stream>>>(feats, N, M, rmax, rsum, cmax, csum,
+  launch_pdl(feats_kernel, dim3((M + 255) / 256, N), 256, 0, stream, det_embeds, memo_embeds, N, M, C, feats);
+  launch_pdl(softmax_stats_kernel, N + M, 128, 0, stream, feats, N, M, rmax, rsum, cmax, csum);
+  launch_pdl(bisoftmax_kernel, static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, stream, feats, N, M, rmax, rsum, cmax, csum,
                                                                                                      det_labels, memo_labels, scores);
   return check_launch("uc_bisoftmax");
 }
 
 extern "C" int uc_box_iou(const float* a, int lda, int N, const float* b, int ldb, int M, float* out, int plus_one, void* stream_v) {
   if (!a || !b || !out || N < 1 || M < 1 || lda < 4 || ldb < 4) return set_error(UC_EINVAL, "uc_box_iou: bad arguments");
-  box_iou_kernel<<<static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(a, lda, N, b, ldb, M, out, plus_one ? 1.f : 0.f);
+  launch_pdl(box_iou_kernel, static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v), a, lda, N, b, ldb, M, out, plus_one ? 1.f : 0.f);
   return check_launch("uc_box_iou");
 }

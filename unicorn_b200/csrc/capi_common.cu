@@ -1,4 +1,5 @@
 // Error reporting, device check and TMA descriptor encoding shared by every entry point.
+#include <stdlib.h>
 #include "uc_common.h"
 #include "../../include/unicorn_b200.h"
 #include <stdarg.h>
@@ -67,6 +68,15 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
   return UC_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UC_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int num_sms() {

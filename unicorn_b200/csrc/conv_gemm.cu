@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   if (CLUSTER > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+  // tail of the previous kernel in the stream; global memory is touched only after it has completed.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ---------------- TMA producer: the whole warp walks the loop (converged), one elected lane issues
@@ -444,13 +448,22 @@ static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CLUSTER;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CLUSTER > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CLUSTER;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "conv_gemm<%d,%d,%d> launch: %s", BLOCK_N, STAGES, CLUSTER, cudaGetErrorString(e));
   return UC_OK;

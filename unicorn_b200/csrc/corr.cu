@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barrier init / TMEM allocation above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // TMA producer: converged warp, one elected lane issues (keeps addresses in uniform registers)
@@ -232,7 +234,7 @@ static int launch_corr(const CorrParams& p, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "corr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  corr_kernel<NOBJ><<<grid, kCorrThreads, smem, stream>>>(p);
+  launch_pdl(corr_kernel<NOBJ>, grid, kCorrThreads, smem, stream, p);
   return check_launch("uc_corr_propagate");
 }
 

@@ -22,6 +22,8 @@ __device__ __forceinline__ void ab_coord(int i, int f, int n, int& i0, int& i1, 
 
 __global__ void __launch_bounds__(256) aligned_bilinear_add_kernel(const uint16_t* __restrict__ src, int lds, int hs, int ws,
                                                                     uint16_t* __restrict__ dst, int ldd, int C, int f) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int C2 = C >> 1, hd = hs * f, wd = ws * f;
   const long total = static_cast<long>(hd) * wd * C2;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -55,6 +57,8 @@ struct MaskLevels {
 __global__ void __launch_bounds__(256) mask_logits_kernel(const float* __restrict__ mask_feats, int h, int w, MaskLevels lv, int ld_dyn,
                                                            const int* __restrict__ anchors, const int* __restrict__ count, int n_max,
                                                            float* __restrict__ logits) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   __shared__ float prm[169];
   __shared__ float inst[3];
   const int n = min(*count, n_max);
@@ -107,6 +111,8 @@ __global__ void __launch_bounds__(256) mask_logits_kernel(const float* __restric
 __global__ void __launch_bounds__(256) mask_convex_up_kernel(const float* __restrict__ logits, const float* __restrict__ up_masks, int h,
                                                               int w, int up, const int* __restrict__ count, int n_max,
                                                               float* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int n = min(*count, n_max);
   const int ins = blockIdx.y;
   if (ins >= n) return;
@@ -135,6 +141,8 @@ __global__ void __launch_bounds__(256) mask_convex_up_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) mask_final_up_kernel(const float* __restrict__ src, int hs, int ws, int f,
                                                              const int* __restrict__ count, int n_max, float* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int n = min(*count, n_max);
   const int ins = blockIdx.y;
   if (ins >= n) return;
@@ -158,7 +166,7 @@ extern "C" int uc_aligned_bilinear_add(const void* src, int lds, int hs, int ws,
   if (!src || !dst || C % 2 || lds % 2 || ldd % 2 || factor < 1) return set_error(UC_EINVAL, "uc_aligned_bilinear_add: bad arguments");
   const long total = static_cast<long>(hs) * factor * ws * factor * (C / 2);
   const int grid = static_cast<int>(std::max<long>(1, std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16)));
-  aligned_bilinear_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(static_cast<const uint16_t*>(src), lds, hs, ws,
+  launch_pdl(aligned_bilinear_add_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), static_cast<const uint16_t*>(src), lds, hs, ws,
                                                                                      static_cast<uint16_t*>(dst), ldd, C, factor);
   return check_launch("uc_aligned_bilinear_add");
 }
@@ -181,13 +189,13 @@ extern "C" int uc_dynamic_masks(const float* mask_feats, const float* up_masks, 
   }
   float* logits = scratch;                                   // [n_max, h, w]
   float* mid = scratch + static_cast<long>(n_max) * h * w;    // [n_max, h*up, w*up]
-  mask_logits_kernel<<<dim3((h * w + 255) / 256, n_max), 256, 0, stream>>>(mask_feats, h, w, lv, ld_dyn, anchors_dev, count_dev, n_max, logits);
+  launch_pdl(mask_logits_kernel, dim3((h * w + 255) / 256, n_max), 256, 0, stream, mask_feats, h, w, lv, ld_dyn, anchors_dev, count_dev, n_max, logits);
   const int H1 = h * up_rate, W1 = w * up_rate;
-  mask_convex_up_kernel<<<dim3((H1 * W1 + 255) / 256, n_max), 256, 0, stream>>>(logits, up_masks, h, w, up_rate, count_dev, n_max,
+  launch_pdl(mask_convex_up_kernel, dim3((H1 * W1 + 255) / 256, n_max), 256, 0, stream, logits, up_masks, h, w, up_rate, count_dev, n_max,
                                                                                 d_rate == 1 ? out_masks : mid);
   if (d_rate != 1) {
     const int H2 = H1 * d_rate, W2 = W1 * d_rate;
-    mask_final_up_kernel<<<dim3((H2 * W2 + 255) / 256, n_max), 256, 0, stream>>>(mid, H1, W1, d_rate, count_dev, n_max, out_masks);
+    launch_pdl(mask_final_up_kernel, dim3((H2 * W2 + 255) / 256, n_max), 256, 0, stream, mid, H1, W1, d_rate, count_dev, n_max, out_masks);
   }
   return check_launch("uc_dynamic_masks");
 }

@@ -9,6 +9,8 @@ namespace uc {
 // yolo_pafpn_new.py:62,139-146 (nn.Upsample nearest x2 + torch.cat) when up == 2; plain slice copy when up == 1.
 __global__ void __launch_bounds__(256) copy_upsample_kernel(const uint16_t* __restrict__ src, int lds, uint16_t* __restrict__ dst,
                                                              int ldd, int B, int Hs, int Ws, int C, int up) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int C8 = C >> 3;
   const int Hd = Hs * up, Wd = Ws * up;
   const long total = static_cast<long>(B) * Hd * Wd * C8;
@@ -29,6 +31,8 @@ __global__ void __launch_bounds__(256) copy_upsample_kernel(const uint16_t* __re
 // unicorn.py:41.  16-bit elements; one thread per output (pixel, channel pair).
 __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const uint16_t* __restrict__ in, int ldi, uint16_t* __restrict__ out,
                                                               int ldo, int B, int H, int W, int Co) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int Co2 = Co >> 1;
   const long total = static_cast<long>(B) * 2 * H * 2 * W * Co2;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -51,6 +55,8 @@ __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const uint16_t* __r
 // src = max(0, (dst + 0.5) * scale - 0.5), scale = Hs/Hd (or 1/scale_factor when a scale factor is given — equal here).
 __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int P, int Hs,
                                                         int Ws, int Hd, int Wd, float sh, float sw) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const long total = static_cast<long>(P) * Hd * Wd;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % Wd);
@@ -70,6 +76,8 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__
 // y = a + b (16-bit rows with strides), 8 elements per thread.
 __global__ void __launch_bounds__(256) add_kernel(const uint16_t* __restrict__ a, int lda, const uint16_t* __restrict__ b, int ldb,
                                                    uint16_t* __restrict__ y, int ldy, long M, int C, int dtype) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int C8 = C >> 3;
   const long total = M * C8;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -90,6 +98,8 @@ __global__ void __launch_bounds__(256) add_kernel(const uint16_t* __restrict__ a
 // NCHW fp32 [B,C,H,W] -> NHWC 16-bit [B,H,W,C] and back (API boundary conversions; C % 2 == 0).
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int ldd, int B,
                                                             int C, long HW, int dtype) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long p0 = static_cast<long>(blockIdx.x) * 32;
@@ -109,6 +119,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint16_t* __restrict__ src, int lds, float* __restrict__ dst, int B,
                                                             int C, long HW, int dtype) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long p0 = static_cast<long>(blockIdx.x) * 32;
@@ -138,7 +150,7 @@ using namespace uc;
 extern "C" int uc_copy_upsample(const void* src, int lds, void* dst, int ldd, int B, int Hs, int Ws, int C, int up, void* stream_v) {
   if (!src || !dst || C % 8 || lds % 8 || ldd % 8 || (up != 1 && up != 2)) return set_error(UC_EINVAL, "uc_copy_upsample: bad arguments");
   const long total = static_cast<long>(B) * Hs * up * Ws * up * (C / 8);
-  copy_upsample_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  launch_pdl(copy_upsample_kernel, grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v), 
       static_cast<const uint16_t*>(src), lds, static_cast<uint16_t*>(dst), ldd, B, Hs, Ws, C, up);
   return check_launch("uc_copy_upsample");
 }
@@ -146,7 +158,7 @@ extern "C" int uc_copy_upsample(const void* src, int lds, void* dst, int ldd, in
 extern "C" int uc_pixel_shuffle2(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co, void* stream_v) {
   if (!in || !out || Co % 2 || ldo % 2) return set_error(UC_EINVAL, "uc_pixel_shuffle2: bad arguments");
   const long total = static_cast<long>(B) * 4 * H * W * (Co / 2);
-  pixel_shuffle2_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  launch_pdl(pixel_shuffle2_kernel, grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v), 
       static_cast<const uint16_t*>(in), ldi, static_cast<uint16_t*>(out), ldo, B, H, W, Co);
   return check_launch("uc_pixel_shuffle2");
 }
@@ -156,7 +168,7 @@ extern "C" int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int 
   if (!src || !dst || P <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0) return set_error(UC_EINVAL, "uc_bilinear_f32: bad arguments");
   const long total = static_cast<long>(P) * Hd * Wd;
   // scale_* = 1/scale_factor when the caller used F.interpolate(scale_factor=...), 0 -> size-based ratio
-  bilinear_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  launch_pdl(bilinear_kernel, grid_for(total), 256, 0, static_cast<cudaStream_t>(stream_v), 
       src, dst, P, Hs, Ws, Hd, Wd, scale_h > 0.f ? scale_h : static_cast<float>(Hs) / Hd,
       scale_w > 0.f ? scale_w : static_cast<float>(Ws) / Wd);
   return check_launch("uc_bilinear_f32");
@@ -164,7 +176,7 @@ extern "C" int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int 
 
 extern "C" int uc_add(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long M, int C, int dtype, void* stream_v) {
   if (!a || !b || !y || C % 8 || lda % 8 || ldb % 8 || ldy % 8) return set_error(UC_EINVAL, "uc_add: bad arguments");
-  add_kernel<<<grid_for(M * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  launch_pdl(add_kernel, grid_for(M * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream_v), 
       static_cast<const uint16_t*>(a), lda, static_cast<const uint16_t*>(b), ldb, static_cast<uint16_t*>(y), ldy, M, C, dtype);
   return check_launch("uc_add");
 }
@@ -172,13 +184,13 @@ extern "C" int uc_add(const void* a, int lda, const void* b, int ldb, void* y, i
 extern "C" int uc_nchw_f32_to_nhwc(const float* src, void* dst, int ldd, int B, int C, long HW, int dtype, void* stream_v) {
   if (!src || !dst || ldd < C) return set_error(UC_EINVAL, "uc_nchw_f32_to_nhwc: bad arguments");
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(B));
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(src, static_cast<uint16_t*>(dst), ldd, B, C, HW, dtype);
+  launch_pdl(nchw_to_nhwc_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), src, static_cast<uint16_t*>(dst), ldd, B, C, HW, dtype);
   return check_launch("uc_nchw_f32_to_nhwc");
 }
 
 extern "C" int uc_nhwc_to_nchw_f32(const void* src, int lds, float* dst, int B, int C, long HW, int dtype, void* stream_v) {
   if (!src || !dst || lds < C) return set_error(UC_EINVAL, "uc_nhwc_to_nchw_f32: bad arguments");
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(B));
-  nhwc_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(static_cast<const uint16_t*>(src), lds, dst, B, C, HW, dtype);
+  launch_pdl(nhwc_to_nchw_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), static_cast<const uint16_t*>(src), lds, dst, B, C, HW, dtype);
   return check_launch("uc_nhwc_to_nchw_f32");
 }

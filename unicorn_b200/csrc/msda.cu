@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) msda_f32_kernel(const float* __restrict__
                                                         const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                                                         const float* __restrict__ attn, float* __restrict__ out, int B, int S,
                                                         int M, int D, int L, int Lq, int P) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const long total = static_cast<long>(B) * Lq * M * D;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int d = static_cast<int>(i % D);
@@ -62,6 +64,8 @@ struct MsdaLevels {
 __global__ void __launch_bounds__(256) msda_fused_kernel(const uint2* __restrict__ value, const float* __restrict__ offlog,
                                                           uint2* __restrict__ out, MsdaLevels lv, int M, int L, int P, int Lq,
                                                           int ld_offlog) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // (q, m)
   const int sub = threadIdx.x & 7;
   if (g >= Lq * M) return;
@@ -118,7 +122,7 @@ extern "C" int uc_msda_forward_f32(const float* value, const int64_t* spatial_sh
   if (B <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0) return set_error(UC_EINVAL, "uc_msda_forward_f32: bad sizes");
   const long total = static_cast<long>(B) * Lq * M * D;
   const int grid = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 32));
-  msda_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(value, spatial_shapes, level_start_index, sampling_loc,
+  launch_pdl(msda_f32_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), value, spatial_shapes, level_start_index, sampling_loc,
                                                                          attn_weight, out, B, S, M, D, L, Lq, P);
   return check_launch("uc_msda_forward_f32");
 }
@@ -137,7 +141,7 @@ extern "C" int uc_msda_fused_bf16(const void* value, const float* offlog, int ld
   }
   const int Lq = start;
   const long threads = static_cast<long>(Lq) * M * 8;
-  msda_fused_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  launch_pdl(msda_fused_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v), 
       static_cast<const uint2*>(value), offlog, static_cast<uint2*>(out), lv, M, L, P, Lq, ld_offlog);
   return check_launch("uc_msda_fused_bf16");
 }

@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restr
                                                           const float2* __restrict__ bias, const float2* __restrict__ lnw,
                                                           const float2* __restrict__ lnb, uint32_t* __restrict__ y, int B,
                                                           int H, int W, int C2 /* C/2 */, float eps) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   __shared__ float red[2][kDwPx][32];
   const int segs = (W + kDwPx - 1) / kDwPx;
   const int seg = blockIdx.x % segs;
@@ -188,6 +190,8 @@ template <int CCH>
 __global__ void __launch_bounds__(512, 2) dwconv7_tiled_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, uint16_t* __restrict__ y, int H,
                                                                 int W, int C, int tiles_w) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   // 512 threads = (CCH/2 channel pairs) x (TH rows) x (2 half rows of 8 pixels): 16 accumulators + 14 staged inputs per
   // thread stay in registers (a 16-pixel strip per thread made the compiler re-read shared memory for every tap).
   constexpr int TW = 16, PX = 8, PAIRS = CCH / 2, TH = 512 / (PAIRS * 2), HW_ = TW + 6, HH_ = TH + 6;
@@ -266,6 +270,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
                                                          const float* __restrict__ w, const float* __restrict__ bvec,
                                                          uint16_t* __restrict__ y, int ldy, long M, int C, float eps,
                                                          int dtype) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int lane = threadIdx.x & 31;
   const long m = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -317,6 +323,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
                                                                const float* __restrict__ prior, const float* __restrict__ beta,
                                                                const uint16_t* __restrict__ add2, int ldadd2,
                                                                uint16_t* __restrict__ y2, int ldy2) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   extern __shared__ float sc[];  // [2][C] scale, shift (+ [C] beta)
   const int b = blockIdx.y;
   const int gs = C / G;
@@ -404,7 +412,7 @@ extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* 
   const int threads = (C2 + 31) / 32 * 32;
   const long blocks = static_cast<long>(B) * H * ((W + kDwPx - 1) / kDwPx);
   if (blocks > 0x7fffffffL) return set_error(UC_EINVAL, "uc_dwconv7_ln: too many blocks");
-  dwconv7_ln_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+  launch_pdl(dwconv7_ln_kernel, static_cast<unsigned>(blocks), threads, 0, stream, 
       static_cast<const uint32_t*>(x_bf16), reinterpret_cast<const float2*>(w49), reinterpret_cast<const float2*>(bias),
       reinterpret_cast<const float2*>(lnw), reinterpret_cast<const float2*>(lnb), static_cast<uint32_t*>(y_bf16), B, H, W, C2, eps);
   return check_launch("uc_dwconv7_ln");
@@ -421,11 +429,11 @@ extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bia
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(dwconv7_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     dim3 grid(tiles_w * ((H + 7) / 8), C / 64, B);
-    dwconv7_tiled_kernel<64><<<grid, 512, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    launch_pdl(dwconv7_tiled_kernel<64>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
   } else {
     constexpr int smem = (16 + 6) * 22 * 64 + 49 * 32 * 4;
     dim3 grid(tiles_w * ((H + 15) / 16), C / 32, B);
-    dwconv7_tiled_kernel<32><<<grid, 512, smem, stream>>>(static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    launch_pdl(dwconv7_tiled_kernel<32>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
   }
   return check_launch("uc_dwconv7");
 }
@@ -438,7 +446,7 @@ extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, 
   if (dtype != UC_BF16 && dtype != UC_F16) return set_error(UC_EINVAL, "uc_layernorm: 16-bit dtypes only");
   const long blocks = (M + 7) / 8;
 #define UC_LN(MAXI)                                                                                                      \
-  layernorm_kernel<MAXI><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(                                            \
+  launch_pdl(layernorm_kernel<MAXI>, static_cast<unsigned>(blocks), 256, 0, stream,                                             \
       static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(res), ldres, w, b, static_cast<uint16_t*>(y), ldy, M, C, eps, dtype)
   if (C <= 128) UC_LN(2);
   else if (C <= 256) UC_LN(4);
@@ -462,7 +470,7 @@ extern "C" int uc_groupnorm_apply(const void* x, int ldx, const void* stats, con
   // each block pays C scale/shift computations up front; keep ~2 elements (16 channels) per thread for parallelism
   const int gx = static_cast<int>(std::max<long>(1, std::min<long>((total + 256 * 2 - 1) / (256 * 2), static_cast<long>(num_sms()) * 8)));
   if (C > 4096) return set_error(UC_EINVAL, "uc_groupnorm_apply: C too large");
-  groupnorm_apply_kernel<<<dim3(gx, B), 256, 3 * C * sizeof(float), stream>>>(
+  launch_pdl(groupnorm_apply_kernel, dim3(gx, B), 256, 3 * C * sizeof(float), stream, 
       static_cast<const uint16_t*>(x), ldx, reinterpret_cast<const long long*>(stats), w, b, static_cast<uint16_t*>(y), ldy, HW, C, G,
       eps, act, prior, beta, static_cast<const uint16_t*>(add2), ldadd2, static_cast<uint16_t*>(y2), ldy2);
   return check_launch("uc_groupnorm_apply");

@@ -19,6 +19,8 @@ struct DecodeLevels {
 };
 
 __global__ void __launch_bounds__(256) head_decode_kernel(DecodeLevels lv, float* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lv.total) return;
   int k = 0;
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) head_decode_kernel(DecodeLevels lv, float
 __global__ void __launch_bounds__(1024) det_filter_kernel(const float* __restrict__ pred, int A, int ncls, float conf,
                                                            float* __restrict__ det, unsigned long long* __restrict__ keys,
                                                            int* __restrict__ count, int cap, int* __restrict__ det_anchor) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   __shared__ int warp_cnt[32];
   __shared__ int warp_excl[32];
   __shared__ int base, round_total;
@@ -100,6 +104,8 @@ __global__ void __launch_bounds__(1024) det_filter_kernel(const float* __restric
 
 // ---- sort keys descending (bitonic, one CTA, n2 = power of two >= count; pads with 0 keys)
 __global__ void __launch_bounds__(1024) sort_desc_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap2) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int n = *count;
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
@@ -124,6 +130,8 @@ __global__ void __launch_bounds__(1024) sort_desc_kernel(unsigned long long* __r
 __global__ void __launch_bounds__(256) det_gather_kernel(const float* __restrict__ det, const unsigned long long* __restrict__ keys,
                                                           const int* __restrict__ count, float* __restrict__ sorted,
                                                           const int* __restrict__ det_anchor, int* __restrict__ sorted_anchor) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   const int n = *count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned idx = 0xffffffffu - static_cast<unsigned>(keys[i] & 0xffffffffull);
@@ -155,6 +163,8 @@ __device__ __forceinline__ bool nms_hit(const float4 a, const float4 b, float th
 __global__ void __launch_bounds__(1024) nms_greedy_kernel(const float* __restrict__ sorted, const int* __restrict__ count, float thr,
                                                            float* __restrict__ out, int* __restrict__ out_count, int max_keep,
                                                            const int* __restrict__ sorted_anchor, int* __restrict__ out_anchor) {
+  pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
+  pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   extern __shared__ float4 kept_box[];                       // [kNmsKeepSmem]
   float* kept_cls = reinterpret_cast<float*>(kept_box + kNmsKeepSmem);  // [kNmsKeepSmem]
   __shared__ float4 cbox[kNmsChunk];
@@ -267,7 +277,7 @@ extern "C" int uc_head_decode(const float* const* regobj, const float* const* cl
     start += lv.h[k] * lv.w[k];
   }
   lv.ld_ro = ld_ro; lv.ld_cls = ld_cls; lv.ncls = ncls; lv.total = start;
-  head_decode_kernel<<<(start + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(lv, out);
+  launch_pdl(head_decode_kernel, (start + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_v), lv, out);
   return check_launch("uc_head_decode");
 }
 
@@ -292,16 +302,16 @@ extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thr
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sorted + static_cast<long>(A) * 7);
   int* det_anchor = reinterpret_cast<int*>(keys + a2);
   int* sorted_anchor = det_anchor + A;
-  det_filter_kernel<<<1, 1024, 0, stream>>>(pred, A, ncls, conf_thre, det, keys, count, A, det_anchor);
-  sort_desc_kernel<<<1, 1024, 0, stream>>>(keys, count, static_cast<int>(a2));
-  det_gather_kernel<<<std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream>>>(det, keys, count, sorted, det_anchor, sorted_anchor);
+  launch_pdl(det_filter_kernel, 1, 1024, 0, stream, pred, A, ncls, conf_thre, det, keys, count, A, det_anchor);
+  launch_pdl(sort_desc_kernel, 1, 1024, 0, stream, keys, count, static_cast<int>(a2));
+  launch_pdl(det_gather_kernel, std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream, det, keys, count, sorted, det_anchor, sorted_anchor);
   constexpr int smem = kNmsKeepSmem * (16 + 4);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  nms_greedy_kernel<<<1, 1024, smem, stream>>>(sorted, count, nms_thre, out_dets, out_count, max_keep > 0 ? max_keep : 0x7fffffff,
+  launch_pdl(nms_greedy_kernel, 1, 1024, smem, stream, sorted, count, nms_thre, out_dets, out_count, max_keep > 0 ? max_keep : 0x7fffffff,
                                                sorted_anchor, out_anchor);
   return check_launch("uc_postprocess");
 }

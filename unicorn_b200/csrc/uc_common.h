@@ -17,6 +17,28 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
                 const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 int check_launch(const char* what);
 int num_sms();
+bool pdl_enabled();  // UC_PDL=0 in the environment turns programmatic dependent launch off (plain stream order)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may become resident while its predecessor in
+// the stream is still draining; every kernel launched this way calls pdl_wait() before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // GroupNorm statistics are accumulated as 64-bit fixed point (value * 2^22) with integer atomics so that the result
 // does not depend on the order in which CTAs finish (bit-reproducible frames).
