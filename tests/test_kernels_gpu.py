@@ -32,11 +32,13 @@ def test_stem(C0, H, W):
     close(out, ref, 6e-3, "stem")
 
 
-@pytest.mark.parametrize("C,H,W", [(96, 20, 28), (192, 17, 23), (256, 10, 16), (1536, 5, 9), (384, 8, 8)])
-def test_dwconv_ln(C, H, W):
+@pytest.mark.parametrize("C,H,W,B", [(96, 20, 28, 2), (192, 17, 23, 2), (256, 10, 16, 2), (1536, 5, 9, 2), (384, 8, 8, 2),
+                                     # the four tile shapes of the fused kernel: 16x8, 8x8, 8x4, 4x2 pixels per CTA
+                                     (192, 64, 120, 2), (384, 100, 160, 1), (768, 60, 100, 2), (768, 50, 80, 1), (1536, 25, 40, 1)])
+def test_dwconv_ln(C, H, W, B):
     from unicorn_b200 import ops
     g = G(2)
-    x = torch.randn(2, H, W, C, generator=g).to(dev).bfloat16()
+    x = torch.randn(B, H, W, C, generator=g).to(dev).bfloat16()
     w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev)
     b, lw, lb = (torch.randn(C, generator=g).to(dev) for _ in range(3))
     out = ops.dwconv7_ln(x, ops.pack_dw_weight(w), b, lw, lb)

@@ -12,6 +12,7 @@ SHAPES = [
     ("s2.pw2", 1, 100, 160, 1536, 384, 1, 1, dict(res=1)),
     ("s3.pw1", 1, 50, 80, 768, 3072, 1, 1, dict(gelu=1)),
     ("s3.pw2", 1, 50, 80, 3072, 768, 1, 1, dict(res=1)),
+    ("s3.plain1", 1, 50, 80, 768, 3072, 1, 1, dict()),      # s3.pw1 without the GELU: what the epilogue math costs
     ("s4.pw1", 1, 25, 40, 1536, 6144, 1, 1, dict(gelu=1)),
     ("s4.pw2", 1, 25, 40, 6144, 1536, 1, 1, dict(res=1)),
     ("down2", 1, 100, 160, 384, 768, 2, 2, dict()),

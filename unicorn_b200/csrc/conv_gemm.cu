@@ -13,6 +13,7 @@
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue.
 // Reference call sites replaced: see include/unicorn_b200.h (uc_conv2d).
 #include <algorithm>
+#include <stdlib.h>
 #include "uc_ptx.cuh"
 #include "uc_common.h"
 #include "../../include/unicorn_b200.h"
@@ -46,7 +47,8 @@ struct alignas(64) ConvKernelParams {
   int ldres;
   void* y;
   int ldy, y_dtype, act;
-  int wide_store, wide_res;  // 256-bit stores / residual loads possible (32-byte aligned rows)
+  int wide_store, wide_res;
+  int debug;  // tools only (UC_CONV_DEBUG): 1 = no MMA (operand feed rate alone), 2 = no TMA loads (MMA + epilogue alone)  // 256-bit stores / residual loads possible (32-byte aligned rows)
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -203,11 +205,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
-            if (CLUSTER > 1) {
+            if (CLUSTER > 1 && p.debug == 2) {
+              if (crank == 0) mbar_arrive(&full[stage]);
+            } else if (CLUSTER > 1) {
               // the leader arms its barrier for the bytes of both CTAs; the peer's loads are credited to it as well
               if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + B_BYTES));
               tma_load_4d_2sm(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
               tma_load_3d_2sm(sB + stage * B_BYTES, &p.tmBh, &full[stage], kc * kBlockK, tp.tap, n0 + crank * (BLOCK_N / 2));
+            } else if (p.debug == 2) {
+              mbar_arrive(&full[stage]);
             } else {
               mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
               tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
@@ -233,7 +239,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (elect_one()) {
+          if (CLUSTER == 1 && p.debug == 1) {
+            if (elect_one()) {
+              mbar_arrive(&empty[stage]);
+              if (it == kiters - 1) mbar_arrive(&tmem_full[acc]);
+            }
+          } else if (elect_one()) {
             // descriptor start address is in 16-byte units: stage offsets and the 32-byte K step are plain adds
             const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * kABytes) >> 4);
             const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_BYTES) >> 4);
@@ -590,6 +601,11 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
     p.wide_res = d->res && ((d->ldres * es) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->res) % 32 == 0);
   }
   p.Cout = d->Cout;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("UC_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res; p.ldres = d->ldres;
   p.y = d->y; p.ldy = d->ldy; p.y_dtype = d->y_dtype; p.act = d->act;

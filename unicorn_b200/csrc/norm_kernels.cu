@@ -262,6 +262,144 @@ __global__ void __launch_bounds__(512, 2) dwconv7_tiled_kernel(const uint16_t* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dwconv7 + LayerNorm (fused)
+// ConvNeXt block head (convnext.py:43-45, 48): y = LN_C(dwconv7x7(x) + bias).  One CTA owns a TW x TH pixel tile and ALL C
+// channels of it: it walks the channels in chunks of 64, staging each chunk's (TW+6) x (TH+6) halo tile and its 49 x 64
+// filter taps with cp.async (double buffered: chunk k+1 streams in while chunk k is computed), computes the depthwise
+// outputs with packed FFMA2 (channel pairs) and parks them as bf16 in a [pixels][C] shared-memory buffer; a second phase
+// does the (two-pass, fp32) LayerNorm of every pixel from that buffer and writes full 128-byte lines.  The intermediate
+// map never exists in global memory and the two launches of the unfused path (uc_dwconv7 + uc_layernorm) become one.
+// The rounding points are the same as the unfused path (conv output rounded to bf16 before the LayerNorm).
+template <int TW, int TH, int PX, int NT>
+__global__ void __launch_bounds__(NT) dwln_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, const float* __restrict__ lnw,
+                                                   const float* __restrict__ lnb, uint16_t* __restrict__ y, int H, int W, int C,
+                                                   int tiles_w, float eps) {
+  constexpr int CCH = 64, PAIRS = 32, HW_ = TW + 6, HH_ = TH + 6, PIX_BYTES = CCH * 2, P = TW * TH, GW = TW / PX;
+  static_assert(GW * TH * PAIRS == NT, "one thread per (channel pair, PX-pixel group)");
+  constexpr int HALO_BYTES = HH_ * HW_ * PIX_BYTES, W_BYTES = 49 * CCH * 4;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint32_t* outb = reinterpret_cast<uint32_t*>(dsm + 2 * HALO_BYTES + 2 * W_BYTES);  // [P][C/2] bf16 pairs
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int ow0 = (blockIdx.x % tiles_w) * TW, oh0 = (blockIdx.x / tiles_w) * TH;
+  const uint16_t* xb = x + static_cast<long>(b) * H * W * C;
+  const int C2 = C >> 1, nchunks = C / CCH;
+
+  auto load_chunk = [&](int k, int buf) {
+    uint8_t* tile = dsm + buf * HALO_BYTES;
+    uint8_t* swb = dsm + 2 * HALO_BYTES + buf * W_BYTES;
+    const int c0 = k * CCH;
+    for (int i = threadIdx.x; i < HH_ * HW_ * 8; i += NT) {
+      const int ch = i & 7, px = i >> 3;
+      const int hx = px % HW_, hy = px / HW_;
+      const int ih = oh0 + hy - 3, iw = ow0 + hx - 3;
+      uint8_t* dst = tile + px * PIX_BYTES + ch * 16;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const uint16_t* src = xb + (static_cast<long>(ih) * W + iw) * C + c0 + ch * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    for (int i = threadIdx.x; i < 49 * 16; i += NT) {
+      const int tap = i >> 4, u = i & 15;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(swb + tap * 256 + u * 16))),
+                   "l"(w + static_cast<long>(tap) * C + c0 + u * 4)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int cp = threadIdx.x % PAIRS;
+  const int grp = threadIdx.x / PAIRS;
+  const int gx = grp % GW, r = grp / GW;
+  load_chunk(0, 0);
+#pragma unroll 1
+  for (int k = 0; k < nchunks; ++k) {
+    const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + k * CCH) + cp);
+    if (k + 1 < nchunks) {
+      load_chunk(k + 1, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* tile = dsm + (k & 1) * HALO_BYTES;
+    const float* sw = reinterpret_cast<const float*>(dsm + 2 * HALO_BYTES + (k & 1) * W_BYTES);
+    unsigned long long acc[PX];
+    {
+      const unsigned long long bb = (static_cast<unsigned long long>(__float_as_uint(bv.y)) << 32) | __float_as_uint(bv.x);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) acc[p] = bb;
+    }
+#pragma unroll 1
+    for (int kh = 0; kh < 7; ++kh) {
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + ((r + kh) * HW_ + gx * PX) * PIX_BYTES) + cp;
+      unsigned long long v[PX + 6];
+#pragma unroll
+      for (int j = 0; j < PX + 6; ++j) {
+        const uint32_t u = rowp[j * (PIX_BYTES / 4)];
+        v[j] = (static_cast<unsigned long long>(u & 0xffff0000u) << 32) | (u << 16);  // (lo -> .x, hi -> .y) as fp32 bits
+      }
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        const unsigned long long wv = *reinterpret_cast<const unsigned long long*>(sw + (kh * 7 + kw) * CCH + 2 * cp);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[p]) : "l"(v[p + kw]), "l"(wv));
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      outb[(r * TW + gx * PX + p) * C2 + k * PAIRS + cp] =
+          pack_bf16(__uint_as_float(static_cast<uint32_t>(acc[p] & 0xffffffffull)), __uint_as_float(static_cast<uint32_t>(acc[p] >> 32)));
+    }
+    __syncthreads();  // chunk k's buffers may be refilled (iteration k+1 prefetches chunk k+2 into them)
+  }
+  // ---- LayerNorm over the channels of every pixel of the tile: one warp per pixel, two-pass statistics in fp32
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_c = 1.f / static_cast<float>(C);
+  for (int px = warp; px < P; px += NT / 32) {
+    const int ow = ow0 + px % TW, oh = oh0 + px / TW;
+    if (ow >= W || oh >= H) continue;
+    const uint32_t* row = outb + px * C2;
+    float s = 0.f;
+    for (int c = lane; c < C2; c += 32) { const uint32_t u = row[c]; s += bf16lo(u) + bf16hi(u); }
+    const float mean = warp_sum(s) * inv_c;
+    float qv = 0.f;
+    for (int c = lane; c < C2; c += 32) {
+      const uint32_t u = row[c];
+      const float d0 = bf16lo(u) - mean, d1 = bf16hi(u) - mean;
+      qv = fmaf(d0, d0, qv);
+      qv = fmaf(d1, d1, qv);
+    }
+    const float rstd = rsqrtf(warp_sum(qv) * inv_c + eps);
+    uint32_t* yr = reinterpret_cast<uint32_t*>(y + ((static_cast<long>(b) * H + oh) * W + ow) * C);
+    for (int c = lane; c < C2; c += 32) {
+      const uint32_t u = row[c];
+      const float2 gw = __ldg(reinterpret_cast<const float2*>(lnw) + c), gb = __ldg(reinterpret_cast<const float2*>(lnb) + c);
+      yr[c] = pack_bf16((bf16lo(u) - mean) * rstd * gw.x + gb.x, (bf16hi(u) - mean) * rstd * gw.y + gb.y);
+    }
+  }
+}
+
+template <int TW, int TH, int PX, int NT>
+static bool launch_dwln(const void* x, const float* w49, const float* bias, const float* lnw, const float* lnb, void* y, int B, int H,
+                        int W, int C, float eps, cudaStream_t stream, bool force) {
+  constexpr int smem_fixed = 2 * (TH + 6) * (TW + 6) * 128 + 2 * 49 * 64 * 4;
+  const int smem = smem_fixed + TW * TH * C * 2;
+  const int tiles_w = (W + TW - 1) / TW, tiles = tiles_w * ((H + TH - 1) / TH);
+  if (smem > 227 * 1024) return false;
+  if (!force && static_cast<long>(tiles) * B < 100) return false;  // too few CTAs for 148 SMs: try a smaller tile
+  static int smem_set = 0;
+  auto kern = dwln_kernel<TW, TH, PX, NT>;
+  if (smem > smem_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
+  launch_pdl(kern, dim3(tiles, B), NT, smem, stream, static_cast<const uint16_t*>(x), w49, bias, lnw, lnb, static_cast<uint16_t*>(y), H, W, C,
+             tiles_w, eps);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm rows
 // y[m, :] = LN(x[m, :] (+ r[m, :])) * w + b, one warp per row, C <= 2048, C even.  x/r/y 16-bit rows with strides.
 template <int MAXI>  // bf16 pairs per lane: C <= 64 * MAXI
@@ -407,7 +545,17 @@ extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* 
                              void* y_bf16, int B, int H, int W, int C, float eps, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!x_bf16 || !w49 || !bias || !lnw || !lnb || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7_ln: null pointer");
+  if (x_bf16 == y_bf16) return set_error(UC_EINVAL, "uc_dwconv7_ln: not an in-place operation");
   if (C % 2 || C > 1536 || C < 2) return set_error(UC_EINVAL, "uc_dwconv7_ln: C must be even and <= 1536");
+  if (C % 64 == 0) {
+    // largest pixel tile that still gives every SM a CTA and fits its [pixels][C] buffer in shared memory
+    bool ok = launch_dwln<16, 8, 8, 512>(x_bf16, w49, bias, lnw, lnb, y_bf16, B, H, W, C, eps, stream, false) ||
+              launch_dwln<8, 8, 8, 256>(x_bf16, w49, bias, lnw, lnb, y_bf16, B, H, W, C, eps, stream, false) ||
+              launch_dwln<8, 4, 4, 256>(x_bf16, w49, bias, lnw, lnb, y_bf16, B, H, W, C, eps, stream, false) ||
+              launch_dwln<4, 2, 1, 256>(x_bf16, w49, bias, lnw, lnb, y_bf16, B, H, W, C, eps, stream, true);
+    if (!ok) return set_error(UC_EINVAL, "uc_dwconv7_ln: no tile configuration fits (C=%d)", C);
+    return check_launch("uc_dwconv7_ln");
+  }
   const int C2 = C / 2;
   const int threads = (C2 + 31) / 32 * 32;
   const long blocks = static_cast<long>(B) * H * ((W + kDwPx - 1) / kDwPx);

@@ -244,6 +244,9 @@ class UnicornEngine:
     def convnext_block(self, x, bp, tag):
         """In place on x (NHWC contiguous) — convnext.py:41-54."""
         B, H, W, C = x.shape
+        # two launches: the channel-chunked tiled depthwise kernel + a row LayerNorm on the L2-resident result.  The fused
+        # one-CTA-per-pixel-tile kernel (ops.dwconv7_ln) was measured slower on every stage of ConvNeXt-L (34.6 vs 28 us on
+        # stage 3: 2.3x the instructions per output, 8 warps per SM) — see DESIGN.md 4.3.
         t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape))
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
         hid = self.conv(t, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
