@@ -148,6 +148,10 @@ def cpu_baseline_sample(cfg, H, W, budget_s=25.0):
             "sample": f"{n} full {H}x{W} SOT frame(s) after 1 warm-up frame, oracle (torch CPU fp32), {cores} threads"}
 
 
+def pk_burst():
+    return peaks()["tf_burst"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,6 +242,43 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) / 1e3)
     t_corr = sorted(ts)[len(ts) // 2]
+    # ---------------- dominant kernel: conv_gemm on the two stage-3 pointwise GEMM shapes (54 of the 172 conv launches of
+    # a frame, 37 % of its device time), timed the way the frame runs them: kernel nodes of a CUDA graph, CUDA events.
+    conv_roof = None
+    if "large" in args.config and (H, W) == (800, 1280):
+        xs = torch.randn(1, 50, 80, 768, device=dev).bfloat16()
+        w1 = ops.pack_conv_weight(torch.randn(3072, 768, 1, 1, device=dev) / 768 ** 0.5)
+        w2 = ops.pack_conv_weight(torch.randn(768, 3072, 1, 1, device=dev) / 3072 ** 0.5)
+        b1, b2, gm = torch.randn(3072, device=dev), torch.randn(768, device=dev), torch.randn(768, device=dev)
+        hid = torch.empty(1, 50, 80, 3072, device=dev, dtype=torch.bfloat16)
+        res = torch.randn(1, 50, 80, 768, device=dev).bfloat16()
+        yo = torch.empty_like(res)
+
+        def pair():
+            eng.conv(xs, w1, 1, bias=b1, act=ops.ACT_GELU, out=hid)
+            eng.conv(hid, w2, 1, bias=b2, gamma=gm, res=res, out=yo)
+        pair()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10):
+                pair()
+        g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        t_pair = a.elapsed_time(b) / 1e3 / 30  # seconds per (pwconv1 + pwconv2)
+        fl = 2 * 2.0 * 4000 * 768 * 3072
+        conv_roof = {"bound": "tensor", "achieved": fl / t_pair / 1e12, "peak": pk_burst(), "unit": "TFLOP/s",
+                     "frac": fl / t_pair / 1e12 / pk_burst(), "us_per_launch": t_pair * 1e6 / 2,
+                     "traffic": 35.5e6, "traffic_note": "ncu --set full, pwconv2 launch, cold L2: 35.5 MB DRAM = A 24.6 + W 4.7 + residual 6.1 "
+                                "(the algorithmic bytes); profiles/r1_ncu_prof_conv_s3pw2.csv",
+                     "kernel": "uc::conv_gemm_kernel, ConvNeXt-L stage-3 pwconv1 (768->3072, GELU) + pwconv2 (3072->768, layer-scale + residual), "
+                               "M = 4000 pixels, CUDA-graph nodes",
+                     "peak_source": "measured bf16_tflops (burst)"}
 
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e], device=dev, dtype=torch.float64)
@@ -264,7 +305,8 @@ def main():
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
                      "traffic": None, "kernel": "whole-frame CUDA graph (1997 GFLOP algorithmic per 800x1280 frame, SURVEY §8d)",
                      "peak_source": pk["src"] + " bf16_tflops_sustained"},
-        "roofline_corr": {"bound": "tensor", "achieved": CORR_GFLOP(n_pos) / t_corr / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+        "roofline_conv": conv_roof,
+        "roofline_corr": {"bound": "tensor", "traffic": 8.28e6, "achieved": CORR_GFLOP(n_pos) / t_corr / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                           "frac": CORR_GFLOP(n_pos) / t_corr / 1e3 / pk["tf_burst"], "us_per_launch": t_corr * 1e6,
                           "hbm_gbs_algorithmic": CORR_BYTES(n_pos) / t_corr / 1e9, "hbm_frac": CORR_BYTES(n_pos) / t_corr / 1e9 / pk["hbm"],
                           "kernel": "uc::corr_kernel<1> (fused K^TQ + softmax + PV), L2 flushed between launches",

@@ -89,6 +89,39 @@ def test_mot_driver_runs_and_is_consistent():
     assert mot.tracker.num_tracklets >= 1
 
 
+def test_mot_pipelined_graph_matches_sequential():
+    """submit(t+1) before collect(t), device half replayed from CUDA graphs: identical detections, embeddings and track
+    ids as the sequential eager protocol (nothing on the device depends on the association)."""
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.mot import UnicornMOTTracker
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    from unicorn_b200.weights import make_state_dict
+    name = "unicorn_track_tiny"
+    eng = UnicornEngine(make_state_dict(name, 0), name)
+    frames, _ = make_video(7, 320, 320, seed=2, n_obj=3)
+    mk = lambda **kw: UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7, score_thr=0.02,  # noqa: E731
+                                        tracker=QuasiDenseEmbedTracker(init_score_thr=0.05, obj_score_thr=0.03), **kw)
+    seq = mk()
+    ref = []
+    for t in range(7):
+        b, i = seq.step_tensor(frames[t:t + 1])
+        ref.append((b.clone(), i.clone(), seq.last["dets"].clone(), seq.last["feats"].clone()))
+    pipe = mk(use_graph=True)
+    got = []
+    pipe.submit(frames[0:1])
+    for t in range(7):
+        if t + 1 < 7:
+            pipe.submit(frames[t + 1:t + 2])
+        b, i = pipe.collect()
+        got.append((b.clone(), i.clone(), pipe.last["dets"].clone(), pipe.last["feats"].clone()))
+    assert len(pipe._graphs) == 2
+    for t, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r[2], g[2]), f"frame {t}: detections differ"
+        assert torch.equal(r[3], g[3]), f"frame {t}: embeddings differ"
+        assert torch.equal(r[1], g[1]) and torch.equal(r[0], g[0]), f"frame {t}: tracks differ"
+
+
 def test_byte_tracker_matches_reference_logic():
     """30 frames of seeded detections through BYTETracker.update vs the reference's own update() flow
     (tests/golden/byte_tracker.npz: reference STrack/Kalman/association code with lap/cython_bbox emulated)."""

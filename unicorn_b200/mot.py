@@ -1,9 +1,19 @@
 """MOT per-frame driver on the B200 engine — the per-frame body of MOTEvaluator.evaluate_omni
 (unicorn/evaluators/mot_evaluator.py:985-1057): `model(imgs, mode="whole")` -> postprocess -> score filter ->
 interaction with the previous frame -> embedding upsample (current frame only) -> embedding sampling at the box
-centres -> QuasiDenseEmbedTracker.match.  The reference's per-box Python grid_sample loop, deepcopy of the frame
-dict and empty_cache() calls are gone; the previous frame's projected tokens are kept in the encoder's token buffer
-(rows of level 0) by swapping two token buffers instead of re-projecting."""
+centres -> QuasiDenseEmbedTracker.match; with `assoc="byte"` the association is BYTETracker.update on the NMS output
+(mot_evaluator.py:177-209, the ByteTrack arm of the evaluator) and the embedding branch is skipped.
+
+The reference's per-box Python grid_sample loop, deepcopy of the frame dict and empty_cache() calls are gone.  The frame
+is split in a device half and a host half:
+
+  submit(frame)  enqueues every kernel of the frame (optionally as ONE CUDA-graph replay), then asynchronous copies of
+                 (count, detections, sampled embeddings) into a pinned result slot, and records an event;
+  collect()      waits for the oldest slot's event and runs the association on the host.
+
+Nothing on the device depends on the association (the previous frame's s16 feature is the only carried state), so
+`submit(t+1); collect(t)` overlaps the host association of frame t with the device work of frame t+1 — same results as
+the sequential `step_tensor`, throughput max(device, host) instead of their sum."""
 import torch
 
 from . import ops
@@ -12,45 +22,107 @@ from .tracker import QuasiDenseEmbedTracker
 
 
 class UnicornMOTTracker:
-    def __init__(self, engine: UnicornEngine, input_size, conf=0.01, nms=0.7, score_thr=0.1, max_dets=1024, tracker=None):
+    def __init__(self, engine: UnicornEngine, input_size, conf=0.01, nms=0.7, score_thr=0.1, max_dets=1024, tracker=None,
+                 assoc="qd", use_graph=False):
+        assert assoc in ("qd", "byte")
         self.eng, self.input_size = engine, tuple(input_size)
         self.conf, self.nms, self.score_thr, self.max_dets = conf, nms, score_thr, max_dets
-        self.tracker = tracker or QuasiDenseEmbedTracker(device=engine.dev)
+        self.assoc = assoc
+        self.tracker = tracker if tracker is not None else (QuasiDenseEmbedTracker(device=engine.dev) if assoc == "qd" else None)
+        assert self.tracker is not None, "assoc='byte' needs a BYTETracker instance"
         H, W = self.input_size
         A = (H // 8) * (W // 8) + (H // 16) * (W // 16) + (H // 32) * (W // 32)
-        self.ws = ops.PostWorkspace(A, engine.dev)
-        self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=engine.dev)
-        self.frame_id = 0
+        dev = engine.dev
+        self.ws = ops.PostWorkspace(A, dev)
+        self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+        self.feats = torch.zeros(max_dets, 128, dtype=torch.float32, device=dev)
+        self.frame_id = 0       # frames submitted
+        self.collected = 0      # frames associated
         self._prev_feat = None
+        # two pinned result slots: at most one frame is in flight behind the one being associated
+        self._slots = [dict(cnt=torch.zeros(1, dtype=torch.int32).pin_memory(), dets=torch.zeros(max_dets, 7).pin_memory(),
+                            feats=torch.zeros(max_dets, 128).pin_memory(), ev=torch.cuda.Event(), scale=1.0, frame_id=0)
+                       for _ in range(2)]
+        self.use_graph = use_graph
+        self._graphs = {}
+        self.last = {}
 
-    def step_tensor(self, frame, scale=1.0):
-        """frame: preprocessed fp32 [1,3,H,W].  Returns (bboxes [n,5] in original-image coordinates, ids [n])."""
+    # ------------------------------------------------------------------------------------------ device half
+    def _device_frame(self, parity):
         e = self.eng
-        self.frame_id += 1
-        self.img_in.copy_(frame, non_blocking=True)
         e.begin_frame()
-        tag = "mot%d" % (self.frame_id & 1)  # two buffer sets: the previous frame's s16 feature must survive
+        tag = "mot%d" % parity  # two buffer sets: the previous frame's s16 feature must survive
         fpn, seq = e.backbone(self.img_in, tag=tag)
         out = e.head(fpn, None, "mot")  # whole mode: zero priors (unicorn.py:133-139)
         dets, cnt = ops.postprocess_device(out[0], e.ncls, self.conf, self.nms, self.ws)
-        prev = self._prev_feat if self._prev_feat is not None else seq["feat"]  # frame 1: pre_dict = cur_dict (:1014-1015)
-        _, f_cur = e.interaction(prev, seq["feat"])
-        emb = e.upsample(f_cur, "mot.emb")
+        emb = None
+        if self.assoc == "qd":
+            prev = self._prev_feat if self._prev_feat is not None else seq["feat"]  # frame 1: pre_dict = cur_dict (:1014-1015)
+            _, f_cur = e.interaction(prev, seq["feat"])
+            emb = e.upsample(f_cur, "mot.emb")
+            ops.sample_embed(emb, dets, self.max_dets, 8.0, count=cnt, out=self.feats)
         self._prev_feat = seq["feat"]
-        n_max = self.max_dets
-        feats = ops.sample_embed(emb, dets, n_max, 8.0, count=cnt)
-        n = min(int(cnt.item()), n_max)
-        d = dets[:n].cpu()
-        f = feats[:n].cpu()
+        self.last = dict(embed=emb, head=out)
+
+    def submit(self, frame, scale=1.0):
+        """frame: preprocessed fp32 [1,3,H,W] (host or device).  Enqueues the frame; returns immediately."""
+        assert self.frame_id - self.collected < 2, "collect() the previous frame first"
+        self.frame_id += 1
+        parity = self.frame_id & 1
+        self.img_in.copy_(frame, non_blocking=True)
+        if self.use_graph and self.frame_id > 2:
+            g = self._graphs.get(parity)
+            if g is None:  # frames 1-2 ran eagerly (plan-time autotuning, first-frame special case); 3 and 4 are captured
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                keep = (self._prev_feat, self.last)
+                with torch.cuda.graph(g):
+                    self._device_frame(parity)
+                self._graphs[parity] = (g, self._prev_feat, self.last)
+                self._prev_feat, self.last = keep
+                g = self._graphs[parity]
+            g[0].replay()
+            self._prev_feat, self.last = g[1], g[2]
+        else:
+            self._device_frame(parity)
+        s = self._slots[parity]
+        n = self.max_dets
+        s["cnt"].copy_(self.ws.count.view(-1)[:1], non_blocking=True)
+        s["dets"].copy_(self.ws.dets[:n], non_blocking=True)
+        if self.assoc == "qd":
+            s["feats"].copy_(self.feats, non_blocking=True)
+        s["scale"], s["frame_id"] = scale, self.frame_id
+        s["ev"].record()
+
+    # ------------------------------------------------------------------------------------------ host half
+    def collect(self, img_info=None):
+        """Association of the oldest submitted frame.  QDTrack: (bboxes [n,5] in original-image coordinates, ids [n]);
+        ByteTrack: the list of active STracks (img_info = (height, width) of the original image)."""
+        assert self.collected < self.frame_id, "nothing submitted"
+        self.collected += 1
+        s = self._slots[self.collected & 1]
+        s["ev"].synchronize()
+        n = min(int(s["cnt"][0]), self.max_dets)
+        d = s["dets"][:n].clone()
+        if self.assoc == "byte":
+            H, W = self.input_size
+            info = img_info if img_info is not None else (H / s["scale"], W / s["scale"])
+            return self.tracker.update(d.numpy(), info, (H, W))
+        f = s["feats"][:n].clone()
         scores = d[:, 4] * d[:, 5]
         keep = scores > self.score_thr  # :1008-1012
-        boxes = torch.cat([d[keep, :4] / scale, scores[keep, None]], 1)
+        boxes = torch.cat([d[keep, :4] / s["scale"], scores[keep, None]], 1)
         labels = torch.ones(boxes.size(0))  # :1013 (all labels = 1)
-        self.last = dict(dets=d, feats=f, embed=emb, head=out)
+        self.last.update(dets=d, feats=f)
         if boxes.size(0) == 0:
             return torch.zeros(0, 5), torch.zeros(0, dtype=torch.long)
-        ob, _, oid = self.tracker.match(boxes, labels, f[keep], self.frame_id)
+        ob, _, oid = self.tracker.match(boxes, labels, f[keep], s["frame_id"])
         valid = oid > -1  # :1047-1053
         ob, oid = ob[valid], oid[valid]
         order = oid.sort()[1]
         return ob[order], oid[order]
+
+    def step_tensor(self, frame, scale=1.0, img_info=None):
+        """Sequential protocol of the reference: one frame in, its tracks out."""
+        self.submit(frame, scale)
+        return self.collect(img_info)

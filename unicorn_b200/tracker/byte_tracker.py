@@ -13,6 +13,7 @@ import torch
 from scipy.optimize import linear_sum_assignment
 
 from .. import ops
+from ._stream import assoc_stream
 
 NEW, TRACKED, LOST, REMOVED = 0, 1, 2, 3
 _STD_POS, _STD_VEL = 1.0 / 20, 1.0 / 160
@@ -118,9 +119,10 @@ def _predict_all(tracks):
 def iou_distance(a_tracks, b_tracks, device):
     if not a_tracks or not b_tracks:
         return np.zeros((len(a_tracks), len(b_tracks)))
-    a = torch.tensor(np.stack([t.tlbr for t in a_tracks]), dtype=torch.float32, device=device)
-    b = torch.tensor(np.stack([t.tlbr for t in b_tracks]), dtype=torch.float32, device=device)
-    return 1.0 - ops.box_iou(a, b, plus_one=True).cpu().numpy().astype(np.float64)
+    with torch.cuda.stream(assoc_stream(device)):  # not behind the next frame's kernels on the main stream
+        a = torch.tensor(np.stack([t.tlbr for t in a_tracks]), dtype=torch.float32, device=device)
+        b = torch.tensor(np.stack([t.tlbr for t in b_tracks]), dtype=torch.float32, device=device)
+        return 1.0 - ops.box_iou(a, b, plus_one=True).cpu().numpy().astype(np.float64)
 
 
 def fuse_score(cost, dets):

@@ -9,6 +9,7 @@ reference's (the eval loop writes them to text files)."""
 import torch
 
 from .. import ops
+from ._stream import assoc_stream
 
 
 class QuasiDenseEmbedTracker:
@@ -42,14 +43,16 @@ class QuasiDenseEmbedTracker:
     def _iou(self, a, b):
         if a.size(0) == 0 or b.size(0) == 0:
             return torch.zeros(a.size(0), b.size(0))
-        return ops.box_iou(a.to(self.dev, torch.float32).contiguous(), b.to(self.dev, torch.float32).contiguous()).cpu()
+        with torch.cuda.stream(assoc_stream(self.dev)):  # not behind the next frame's kernels on the main stream
+            return ops.box_iou(a.to(self.dev, torch.float32).contiguous(), b.to(self.dev, torch.float32).contiguous()).cpu()
 
     def _scores(self, embeds, labels, m_embeds, m_labels):
-        e = embeds.to(self.dev, torch.float32).contiguous()
-        m = m_embeds.to(self.dev, torch.float32).contiguous()
-        ld = labels.to(self.dev, torch.float32).contiguous() if self.with_cats else None
-        lm = m_labels.to(self.dev, torch.float32).contiguous() if self.with_cats else None
-        return ops.bisoftmax(e, m, ld, lm).cpu()
+        with torch.cuda.stream(assoc_stream(self.dev)):
+            e = embeds.to(self.dev, torch.float32).contiguous()
+            m = m_embeds.to(self.dev, torch.float32).contiguous()
+            ld = labels.to(self.dev, torch.float32).contiguous() if self.with_cats else None
+            lm = m_labels.to(self.dev, torch.float32).contiguous() if self.with_cats else None
+            return ops.bisoftmax(e, m, ld, lm).cpu()
 
     # ---------------------------------------------------------------------------------------------- match
     def match(self, bboxes, labels, track_feats, frame_id, asso_tau=-1, return_index=False):
