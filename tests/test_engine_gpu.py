@@ -120,3 +120,41 @@ def test_cuda_graph_replay_matches_eager(setup):
     # the graph tracker stops NMS after max_inst kept boxes: its rows are exactly the head of the full result
     assert n2 == min(setup["n"], 3), (n2, setup["n"])
     assert torch.equal(d2, setup["dets"][:n2]), (d2, setup["dets"])
+
+
+def test_reference_api_facade(setup):
+    """unicorn_b200.compat.model: the reference's stage-by-stage calling convention (unicorn_sot.py:78-109 written out with
+    model(..., mode=...) calls, NCHW fp32 tensors and the plain torch mm + softmax(dim=0) correlation of the reference) on
+    the B200 engine; same tolerances as the fused driver, and seq_dict must survive copy.deepcopy (mot_evaluator.py:1015)."""
+    import copy
+    import torch.nn.functional as F
+    from unicorn_b200.compat.model import UnicornB200Model, postprocess
+    from unicorn_b200.sot import get_label_map
+    st, frames, boxes = setup["st"], setup["frames"], setup["boxes"]
+    model = UnicornB200Model(setup["sd"], "unicorn_track_tiny").eval()
+    ref_img, cur_img = frames[0:1].cuda(), frames[2:3].cuda()
+    _, d0 = model(imgs=ref_img, mode="backbone")
+    d0 = copy.deepcopy(d0)
+    fpn, d1 = model(imgs=cur_img, mode="backbone")
+    assert set(d1) == {"feat", "pos", "h", "w"} and rel(d1["pos"], st["pos"]) < 1e-3
+    f0, f1 = model(seq_dict0=d0, seq_dict1=d1, mode="interaction")
+    e0, e1 = model(feat=f0, mode="upsample"), model(feat=f1, mode="upsample")
+    assert rel(f1, st["inter_cur"]) < 5e-2 and rel(e1, st["embed_cur"]) < 5e-2
+    for i in range(3):
+        assert rel(fpn[i], st["fpn"][i]) < 8e-2
+    lbl = F.interpolate(get_label_map(boxes[0, 0], 320, 320, "cuda"), scale_factor=1 / 8, mode="bilinear", align_corners=False)
+    k, q = e0.half().flatten(-2)[0], e1.half().flatten(-2)[0]          # (C, N) each — unicorn_sot.py:92-97
+    trans = torch.softmax(torch.mm(k.t(), q).float(), dim=0)           # softmax over the reference positions
+    coarse = torch.mm(lbl.view(1, -1).float(), trans).view(1, 1, 40, 40)
+    assert (coarse[0].cpu() - st["coarse"][0]).abs().max().item() < 6e-2
+    pri = [coarse, F.interpolate(coarse, scale_factor=1 / 2, mode="bilinear", align_corners=False),
+           F.interpolate(coarse, scale_factor=1 / 4, mode="bilinear", align_corners=False)]
+    out = model.head(fpn, pri, mode="sot")
+    assert out.shape == st["head"].shape
+    assert (out.cpu()[..., 4:] - st["head"][..., 4:]).abs().max().item() < 5e-2
+    dets = postprocess(out, 1, 0.001, 0.65)[0]
+    assert dets is not None and abs(dets.shape[0] - st["dets"].shape[0]) <= max(5, 0.05 * st["dets"].shape[0])
+    whole, _ = model(imgs=cur_img, mode="whole")
+    assert whole.shape == (1, 2100, 5 + model.num_classes)
+    with pytest.raises(ValueError):
+        model(imgs=cur_img, mode="train")
