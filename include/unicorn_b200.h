@@ -124,6 +124,11 @@ UC_API int uc_pixel_shuffle2(const void* in, int ldi, void* out, int ldo, int B,
 /* F.interpolate(bilinear, align_corners=False) on fp32 planes [P,Hs,Ws]->[P,Hd,Wd]; scale_* = 1/scale_factor or 0. */
 UC_API int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int Ws, int Hd, int Wd, float scale_h,
                            float scale_w, void* stream);
+/* Letterbox preprocessing on the device (PreprocessorX.process, external/lib/test/tracker/unicorn_sot.py:114-123; preproc,
+ * unicorn/data/data_augment.py:194-214): dst[0:rh,0:rw] = cv2.resize(src,(rw,rh),INTER_LINEAR) — bit-exact restatement of
+ * OpenCV's 8-bit fixed-point bilinear —, the rest = pad (114); swap_rb does cv2.COLOR_RGB2BGR.  uint8 HWC, 3 channels. */
+UC_API int uc_letterbox_u8(const uint8_t* src_hwc, int Hs, int Ws, uint8_t* dst_hwc, int Hd, int Wd, int rh, int rw,
+                           int swap_rb, int pad, void* stream);
 UC_API int uc_add(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long M, int C, int dtype, void* stream);
 UC_API int uc_nchw_f32_to_nhwc(const float* src, void* dst, int ldd, int B, int C, long HW, int dtype, void* stream);
 UC_API int uc_nhwc_to_nchw_f32(const void* src, int lds, float* dst, int B, int C, long HW, int dtype, void* stream);

@@ -73,6 +73,55 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ letterbox (preprocessing)
+// PreprocessorX.process (external/lib/test/tracker/unicorn_sot.py:114-123) / preproc (unicorn/data/data_augment.py:194-214):
+// dst[0:rh, 0:rw] = cv2.resize(src, (rw, rh), INTER_LINEAR), everything else = pad (114), optionally RGB -> BGR.
+// Bit-exact restatement of OpenCV's 8-bit bilinear (imgproc/resize.cpp: 11-bit fixed-point coefficients):
+//   per axis  f = float((d + 0.5) * scale - 0.5), s = floor(f), f -= s, coefficients (short)rint((1-f)*2048), rint(f*2048);
+//   x axis: s < 0 -> (s, f) = (0, 0); s >= W-1 -> (W-1, 0).  y axis: f is kept and the two source rows are clamped instead;
+//   horizontal pass  h = S[sx]*a0 + S[sx+1]*a1 (int32);  vertical  (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.
+// One thread per output pixel (3 channels); the frame is read once from HBM (neighbouring threads share the source lines).
+__device__ __forceinline__ void resize_axis(int d, double scale, int ssize, bool clamp, int& s0, int& s1, int& c0, int& c1) {
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s);
+  if (clamp) {
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+  }
+  c0 = __float2int_rn((1.f - f) * 2048.f);
+  c1 = __float2int_rn(f * 2048.f);
+  s0 = min(max(s, 0), ssize - 1);
+  s1 = min(max(s + 1, 0), ssize - 1);
+}
+
+__global__ void __launch_bounds__(256) letterbox_u8_kernel(const uint8_t* __restrict__ src, int Hs, int Ws, uint8_t* __restrict__ dst, int Hd,
+                                                            int Wd, int rh, int rw, double scale_y, double scale_x, int swap_rb, int pad) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long total = static_cast<long>(Hd) * Wd;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % Wd), y = static_cast<int>(i / Wd);
+    uint8_t o[3] = {static_cast<uint8_t>(pad), static_cast<uint8_t>(pad), static_cast<uint8_t>(pad)};
+    if (x < rw && y < rh) {
+      int sx0, sx1, a0, a1, sy0, sy1, b0, b1;
+      resize_axis(x, scale_x, Ws, true, sx0, sx1, a0, a1);
+      resize_axis(y, scale_y, Hs, false, sy0, sy1, b0, b1);
+      const uint8_t* r0 = src + static_cast<long>(sy0) * Ws * 3;
+      const uint8_t* r1 = src + static_cast<long>(sy1) * Ws * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[sx0 * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+        const int h1 = r1[sx0 * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[swap_rb ? 2 - c : c] = static_cast<uint8_t>(v);
+      }
+    }
+    uint8_t* d = dst + i * 3;
+    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+  }
+}
+
 // y = a + b (16-bit rows with strides), 8 elements per thread.
 __global__ void __launch_bounds__(256) add_kernel(const uint16_t* __restrict__ a, int lda, const uint16_t* __restrict__ b, int ldb,
                                                    uint16_t* __restrict__ y, int ldy, long M, int C, int dtype) {
@@ -172,6 +221,17 @@ extern "C" int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int 
       src, dst, P, Hs, Ws, Hd, Wd, scale_h > 0.f ? scale_h : static_cast<float>(Hs) / Hd,
       scale_w > 0.f ? scale_w : static_cast<float>(Ws) / Wd);
   return check_launch("uc_bilinear_f32");
+}
+
+extern "C" int uc_letterbox_u8(const uint8_t* src_hwc, int Hs, int Ws, uint8_t* dst_hwc, int Hd, int Wd, int rh, int rw, int swap_rb,
+                               int pad, void* stream_v) {
+  if (!src_hwc || !dst_hwc || Hs < 1 || Ws < 1 || Hd < 1 || Wd < 1 || rh < 1 || rw < 1 || rh > Hd || rw > Wd || pad < 0 || pad > 255)
+    return set_error(UC_EINVAL, "uc_letterbox_u8: bad arguments");
+  // cv::resize with an explicit dsize: inv_scale = dsize / ssize (double), scale = 1 / inv_scale
+  const double scale_x = 1.0 / (static_cast<double>(rw) / Ws), scale_y = 1.0 / (static_cast<double>(rh) / Hs);
+  launch_pdl(letterbox_u8_kernel, grid_for(static_cast<long>(Hd) * Wd), 256, 0, static_cast<cudaStream_t>(stream_v), src_hwc, Hs, Ws, dst_hwc,
+             Hd, Wd, rh, rw, scale_y, scale_x, swap_rb, pad);
+  return check_launch("uc_letterbox_u8");
 }
 
 extern "C" int uc_add(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long M, int C, int dtype, void* stream_v) {

@@ -207,6 +207,19 @@ def add(a2d, b2d, out=None):
     return out
 
 
+def letterbox_u8(src, input_size, swap_rb=True, pad=114, out=None):
+    """src: uint8 [h,w,3] device tensor (RGB when swap_rb) -> (uint8 [1,H,W,3] letterboxed frame, r) — the preprocessing of
+    external/lib/test/tracker/unicorn_sot.py:114-123 (swap_rb=True) / data_augment.py:194-214 (swap_rb=False)."""
+    assert src.dtype == torch.uint8 and src.is_cuda and src.is_contiguous() and src.dim() == 3 and src.shape[2] == 3
+    h, w = src.shape[:2]
+    H, W = input_size
+    r = min(H / h, W / w)
+    if out is None:
+        out = torch.empty(1, H, W, 3, dtype=torch.uint8, device=src.device)
+    _lib.check(_L().uc_letterbox_u8(_p(src), h, w, _p(out), H, W, int(h * r), int(w * r), int(bool(swap_rb)), int(pad), _S()), "uc_letterbox_u8")
+    return out, r
+
+
 def nchw_to_nhwc(x, dtype=torch.bfloat16, out=None):
     B, C, H, W = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()

@@ -38,11 +38,16 @@ def preprocess(img_rgb, input_size, out=None):
 
 
 class UnicornSOTTrack:
-    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=3, use_graph=True, full_nms=False):
+    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=3, use_graph=True, full_nms=False,
+                 device_preproc=False):
         self.eng, self.input_size = engine, tuple(input_size)
         self.confthre, self.nmsthre, self.max_inst = conf, nms, max_inst
         self.num_classes = 1
         self.use_graph = use_graph
+        # device_preproc: initialize()/track() upload the raw RGB frame and letterbox it on the GPU (uc_letterbox_u8, bit-exact
+        # restatement of the reference's cv2 recipe) instead of resizing on the host
+        self.device_preproc = device_preproc
+        self._raw = None
         # the driver consumes output[:max_inst] only (unicorn_sot.py:69-70): stop the greedy NMS scan there.
         # full_nms=True reproduces the complete postprocess() list (used by the parity tests).
         self.nms_keep = 0 if full_nms else max_inst
@@ -126,15 +131,27 @@ class UnicornSOTTrack:
         return self.host_dets[:min(n, self.max_inst)].clone(), n
 
     # -------------------------------------------------------------------------------- reference protocol
+    def _preprocess(self, image):
+        if not self.device_preproc:
+            return preprocess(image, self.input_size)
+        src = torch.from_numpy(image) if not torch.is_tensor(image) else image
+        assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3
+        if self._raw is None or self._raw.shape != src.shape:
+            self._raw = torch.empty(src.shape, dtype=torch.uint8, device=self.eng.dev)
+            self._raw_host = torch.empty(src.shape, dtype=torch.uint8).pin_memory()
+        self._raw_host.copy_(src)
+        self._raw.copy_(self._raw_host, non_blocking=True)
+        return ops.letterbox_u8(self._raw, self.input_size, swap_rb=True)  # uint8 [1,H,W,3] on the device
+
     def initialize(self, image, info: dict):
-        ref, r = preprocess(image, self.input_size)
+        ref, r = self._preprocess(image)
         box = torch.tensor(info["init_bbox"], dtype=torch.float32).view(-1)
         box[2:] += box[:2]
         self.initialize_tensor(ref, box * r)
         self.state = info["init_bbox"]
 
     def track(self, image, info: dict = None):
-        cur, r = preprocess(image, self.input_size)
+        cur, r = self._preprocess(image)
         dets, n = self.track_tensor(cur)
         if n > 0:
             out = dets.numpy().copy()
