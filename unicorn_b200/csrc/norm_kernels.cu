@@ -482,21 +482,41 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const uint16_t* __
   __syncthreads();
   const int C8 = C >> 3;
   const long total = HW * C8;
+  const bool silu = act == UC_ACT_SILU, relu = act == UC_ACT_RELU;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>(i % C8) * 8;
     const long pix = static_cast<long>(b) * HW + i / C8;
     const uint4 u = *reinterpret_cast<const uint4*>(x + pix * ldx + c0);
     const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+    // per-channel coefficients as 128-bit shared-memory loads (c0 is a multiple of 8 -> 32-byte aligned)
+    const float4 s0 = *reinterpret_cast<const float4*>(sc + c0), s1 = *reinterpret_cast<const float4*>(sc + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(sc + C + c0), h1 = *reinterpret_cast<const float4*>(sc + C + c0 + 4);
+    const float scl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sft[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     float f[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { f[2 * t] = bf16lo(uw[t]); f[2 * t + 1] = bf16hi(uw[t]); }
-    const float pr = prior ? __ldg(prior + pix) : 0.f;
+    for (int t = 0; t < 4; ++t) {
+      f[2 * t] = fmaf(bf16lo(uw[t]), scl[2 * t], sft[2 * t]);
+      f[2 * t + 1] = fmaf(bf16hi(uw[t]), scl[2 * t + 1], sft[2 * t + 1]);
+    }
+    if (silu) {  // x * sigmoid(x) with ex2.approx / rcp.approx (~1 ulp each; the result is rounded to bf16)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = fmaf(f[j], sc[c0 + j], sc[C + c0 + j]);
-      if (act == UC_ACT_SILU) v = v / (1.f + __expf(-v));
-      else if (act == UC_ACT_RELU) v = fmaxf(v, 0.f);
-      f[j] = fmaf(pr, sc[2 * C + c0 + j], v);
+      for (int j = 0; j < 8; ++j) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-f[j] * 1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+        f[j] *= r;
+      }
+    } else if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (prior) {
+      const float pr = __ldg(prior + pix);
+      const float4 b0 = *reinterpret_cast<const float4*>(sc + 2 * C + c0), b1 = *reinterpret_cast<const float4*>(sc + 2 * C + c0 + 4);
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(pr, bt[j], f[j]);
     }
     uint4 o;
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
