@@ -59,7 +59,7 @@ def test_dwconv_tiled(C, H, W):
     close(out, ref, 5e-3, "dwconv tiled")
 
 
-@pytest.mark.parametrize("C", [96, 192, 256, 1536])
+@pytest.mark.parametrize("C", [96, 100, 192, 256, 384, 768, 1536, 2048])  # 100: not a multiple of 8 -> the 32-bit-access kernel
 def test_layernorm(C):
     from unicorn_b200 import ops
     g = G(3)

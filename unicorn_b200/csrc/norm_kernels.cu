@@ -450,6 +450,80 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
   }
 }
 
+// Same LayerNorm with 128-bit accesses: a lane owns 8-channel chunks lane + 32 i (C % 8 == 0, 16-byte aligned rows); the affine
+// parameters of the first chunks are requested before the two warp reductions so that their latency is hidden behind them.
+template <int MAXV>  // 8-channel chunks per lane: C <= 256 * MAXV
+__global__ void __launch_bounds__(256) layernorm_v8_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ r, int ldr,
+                                                            const float* __restrict__ w, const float* __restrict__ bvec,
+                                                            uint16_t* __restrict__ y, int ldy, long M, int C, float eps, int dtype) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const long m = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int C8 = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + m * ldx);
+  const uint4* rr = r ? reinterpret_cast<const uint4*>(r + m * ldr) : nullptr;
+  float v[MAXV][8];
+  constexpr int PRE = MAXV <= 3 ? MAXV : 0;  // chunks whose gamma / beta are prefetched (register budget)
+  float4 gw[PRE > 0 ? PRE : 1][2], gb[PRE > 0 ? PRE : 1][2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    if (c < C8) {
+      const uint4 u = __ldg(xr + c);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { v[i][2 * t] = bits16_to_float(uw[t] & 0xffffu, dtype); v[i][2 * t + 1] = bits16_to_float(uw[t] >> 16, dtype); }
+      if (rr) {
+        const uint4 u2 = __ldg(rr + c);
+        const uint32_t rw[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { v[i][2 * t] += bits16_to_float(rw[t] & 0xffffu, dtype); v[i][2 * t + 1] += bits16_to_float(rw[t] >> 16, dtype); }
+      }
+      if (i < PRE) {
+        gw[i][0] = __ldg(reinterpret_cast<const float4*>(w) + 2 * c); gw[i][1] = __ldg(reinterpret_cast<const float4*>(w) + 2 * c + 1);
+        gb[i][0] = __ldg(reinterpret_cast<const float4*>(bvec) + 2 * c); gb[i][1] = __ldg(reinterpret_cast<const float4*>(bvec) + 2 * c + 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < C8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + m * ldy);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C8) {
+      float4 w0, w1, b0, b1;
+      if (i < PRE) { w0 = gw[i][0]; w1 = gw[i][1]; b0 = gb[i][0]; b1 = gb[i][1]; }
+      else {
+        w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * c); w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * c + 1);
+        b0 = __ldg(reinterpret_cast<const float4*>(bvec) + 2 * c); b1 = __ldg(reinterpret_cast<const float4*>(bvec) + 2 * c + 1);
+      }
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * ww[j] + bb[j];
+      uint4 u;
+      u.x = pack2_16(o[0], o[1], dtype); u.y = pack2_16(o[2], o[3], dtype); u.z = pack2_16(o[4], o[5], dtype); u.w = pack2_16(o[6], o[7], dtype);
+      yr[c] = u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm apply
 // y = act(x * scale[c] + shift[c]) (+ prior[pix] * beta[c]); optional second output y2 = y + add2.
 // scale/shift fold the group statistics (int64 fixed point {sum, sumsq} accumulated by uc_conv2d) with the affine
@@ -613,6 +687,20 @@ extern "C" int uc_layernorm(const void* x, int ldx, const void* res, int ldres, 
   if (C % 2 || C > 2048 || ldx % 2 || ldy % 2 || (res && ldres % 2)) return set_error(UC_EINVAL, "uc_layernorm: C even <= 2048, even strides");
   if (dtype != UC_BF16 && dtype != UC_F16) return set_error(UC_EINVAL, "uc_layernorm: 16-bit dtypes only");
   const long blocks = (M + 7) / 8;
+  const bool v8 = C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!res || ldres % 8 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res)) & 15) == 0;
+  if (v8) {
+#define UC_LNV(MAXV)                                                                                                     \
+  launch_pdl(layernorm_v8_kernel<MAXV>, static_cast<unsigned>(blocks), 256, 0, stream,                                          \
+      static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(res), ldres, w, b, static_cast<uint16_t*>(y), ldy, M, C, eps, dtype)
+    if (C <= 256) UC_LNV(1);
+    else if (C <= 512) UC_LNV(2);
+    else if (C <= 768) UC_LNV(3);
+    else if (C <= 1536) UC_LNV(6);
+    else UC_LNV(8);
+#undef UC_LNV
+    return check_launch("uc_layernorm");
+  }
 #define UC_LN(MAXI)                                                                                                      \
   launch_pdl(layernorm_kernel<MAXI>, static_cast<unsigned>(blocks), 256, 0, stream,                                             \
       static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(res), ldres, w, b, static_cast<uint16_t*>(y), ldy, M, C, eps, dtype)
