@@ -207,12 +207,20 @@ class UnicornEngine:
     def load_tuning(self, path=None):
         """Per-layer N-tile choices measured on a B200 and committed under unicorn_b200/tuned/ (plan-time autotuning
         fills in whatever is missing).  Returns the number of entries loaded."""
+        import glob
         import json
-        path = path or self.tuning_path()
-        if os.path.exists(path):
-            self._bn_cache.update(json.load(open(path)))
-            return len(self._bn_cache)
-        return 0
+        if path is None:
+            # keys are layer shapes, not config names: the tables of the other configs cover the layers they share with this
+            # one (e.g. *_mask and *_mot_challenge differ from unicorn_track_large only in the head outputs); this config's
+            # own table is applied last
+            own = self.tuning_path()
+            paths = sorted(p for p in glob.glob(os.path.join(os.path.dirname(own), "*.json")) if p != own) + [own]
+        else:
+            paths = [path]
+        for p in paths:
+            if os.path.exists(p):
+                self._bn_cache.update(json.load(open(p)))
+        return len(self._bn_cache)
 
     def save_tuning(self, path):
         import json
