@@ -99,3 +99,32 @@ def test_nms_restatement_matches_torchvision():
     out = orc.postprocess(pred, 3, 0.0, 0.65)[0]
     assert out.shape[0] == keep.numel()
     assert torch.allclose(out[:, :4], boxes[keep], atol=1e-4)
+
+
+def test_mask_path_matches_reference_golden():
+    """Config 4 (UnicornHeadMask + CondInst dynamic masks): the oracle's backbone -> interaction -> correlation -> mask head ->
+    postprocess_inst on the tiny mask model against tests/golden/mask_tiny_320.npz (outputs of the UNMODIFIED reference,
+    tests/golden/make_golden_mask.py)."""
+    import torch.nn.functional as F
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mask_tiny_320.npz"))
+    name = str(g["config"])
+    sd = make_state_dict(name, 0)
+    cfg = orc.CONFIGS[name]
+    frames, boxes = make_video(2, 320, 320, seed=0)
+    with torch.no_grad():
+        _, pre = orc.forward_backbone(frames[0:1], sd, cfg)
+        fpn, cur = orc.forward_backbone(frames[1:2], sd, cfg)
+        f_pre, f_cur = orc.deform_interaction(pre, cur, sd)
+        e_pre, e_cur = orc.upsample_embed(f_pre, sd), orc.upsample_embed(f_cur, sd)
+        pred = orc.corr_propagate(e_pre.flatten(-2)[0], e_cur.flatten(-2)[0], orc.label_map_s8(boxes[0, 0], 320, 320))
+        pri = orc.prior_pyramid(pred.view(1, -1, 40, 40))
+        outs, locs, dyn, lvls, mf, um = orc.head_forward_mask(fpn, pri, sd, cfg, "sot")
+        dets, masks = orc.postprocess_inst(outs, locs, dyn, lvls, mf, um, 1, float(g["conf"]), float(g["nms"]), d_rate=2, max_masks=int(g["keep"]))
+    assert rel(mf, g["mask_feats"]) < 1e-4
+    assert rel(um[0, :, ::4, ::4], g["up_masks_sub"]) < 1e-4
+    assert rel(dyn[0, ::16], g["dyn_sub"]) < 1e-4
+    ref = torch.from_numpy(g["dets"])
+    assert dets.shape == ref.shape and rel(dets[:, :6], ref[:, :6]) < 1e-4
+    assert (masks[0, 0, ::2, ::2] - torch.from_numpy(g["mask0_sub"].astype(np.float32))).abs().max().item() < 2e-3  # fixture is fp16
+    area = (masks[:, 0] > 0.5).float().mean(dim=(1, 2)).numpy()
+    assert np.allclose(area, g["mask_area"], atol=1e-4)

@@ -1,0 +1,40 @@
+"""Host logic of the trackers on CPU: BYTETracker.update (track life cycle, two-stage association, batched Kalman, LAP) against
+the reference golden with the IoU KERNEL replaced by a numpy stand-in (the kernel itself is checked on the GPU in
+tests/test_tracker_gpu.py), and the MOT driver's host half (collect) on hand-made result slots."""
+import contextlib
+import os
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _iou_np(a, b, plus_one=False):
+    a, b, p = a.numpy().astype(np.float64), b.numpy().astype(np.float64), (1.0 if plus_one else 0.0)
+    iw = np.clip(np.minimum(a[:, None, 2], b[None, :, 2]) - np.maximum(a[:, None, 0], b[None, :, 0]) + p, 0, None)
+    ih = np.clip(np.minimum(a[:, None, 3], b[None, :, 3]) - np.maximum(a[:, None, 1], b[None, :, 1]) + p, 0, None)
+    aa = (a[:, 2] - a[:, 0] + p) * (a[:, 3] - a[:, 1] + p)
+    bb = (b[:, 2] - b[:, 0] + p) * (b[:, 3] - b[:, 1] + p)
+    return torch.from_numpy((iw * ih / (aa[:, None] + bb[None] - iw * ih)).astype(np.float32))
+
+
+def test_byte_tracker_host_logic_matches_reference_golden(monkeypatch):
+    import unicorn_b200.tracker.byte_tracker as bt
+    from unicorn_b200.synthetic import make_detections
+    monkeypatch.setattr(bt.ops, "box_iou", _iou_np)
+    monkeypatch.setattr(bt, "assoc_stream", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    g = np.load(os.path.join(ROOT, "tests", "golden", "byte_tracker.npz"))
+    args = types.SimpleNamespace(track_thresh=0.6, track_buffer=30, match_thresh=0.9, mot20=False)
+    bt.STrack._count = 0
+    trk = bt.BYTETracker(args, device="cpu")
+    for i, (boxes, _) in enumerate(make_detections(int(g["n_frames"]), int(g["n_obj"]), int(g["seed"]))):
+        out = trk.update(boxes.numpy().copy(), (800, 1280), (800, 1280))
+        rows = np.array([[t.track_id, *t.tlwh, t.score] for t in out]).reshape(-1, 6)
+        rows = rows[np.argsort(rows[:, 0])] if len(rows) else rows
+        ref = g[f"f{i}"]
+        assert rows.shape == ref.shape and np.array_equal(rows[:, 0], ref[:, 0]), (i, rows[:, 0], ref[:, 0])
+        assert np.allclose(rows[:, 1:], ref[:, 1:], rtol=1e-4, atol=1e-2)
+    assert bt.STrack._count == int(g["total_ids"])

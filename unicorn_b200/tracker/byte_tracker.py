@@ -47,6 +47,32 @@ def _kf_update(mean, cov, xyah):
     return mean + innov @ k.T, cov - k @ pc @ k.T
 
 
+def _kf_update_batch(mean, cov, z):
+    """_kf_update for n tracks at once: mean [n,8], cov [n,8,8], z [n,4] (H = [I4 | 0] selects, so H m and H P H^T are slices)."""
+    h = mean[:, 3]
+    r = np.zeros((len(h), 4, 4))
+    idx = np.arange(4)
+    r[:, idx, idx] = np.stack([_STD_POS * h, _STD_POS * h, np.full_like(h, 1e-1), _STD_POS * h], 1) ** 2
+    pc = cov[:, :4, :4] + r
+    k = np.linalg.solve(pc, cov[:, :, :4].transpose(0, 2, 1)).transpose(0, 2, 1)  # [n,8,4]
+    innov = z - mean[:, :4]
+    return mean + np.einsum("ni,nji->nj", innov, k), cov - k @ pc @ k.transpose(0, 2, 1)
+
+
+def _update_matched(pairs, frame_id):
+    """STrack.update for every (track, detection) pair of one association stage with ONE batched Kalman update."""
+    if not pairs:
+        return
+    mean = np.stack([t.mean for t, _ in pairs])
+    cov = np.stack([t.cov for t, _ in pairs])
+    z = np.stack([t.xyah(d.tlwh) for t, d in pairs])
+    mean, cov = _kf_update_batch(mean, cov, z)
+    for i, (t, d) in enumerate(pairs):
+        t.mean, t.cov = mean[i], cov[i]
+        t.tracklet_len = 0 if t.state != TRACKED else t.tracklet_len + 1  # re-activation of a lost track restarts the length
+        t.state, t.is_activated, t.frame_id, t.score = TRACKED, True, frame_id, d.score
+
+
 class STrack:
     _count = 0  # process-wide id counter like BaseTrack._count (basetrack.py:13,34-37)
 
@@ -116,12 +142,28 @@ def _predict_all(tracks):
         t.mean, t.cov = mean[i], cov[i]
 
 
+def _tlbr_all(tracks):
+    """np.stack([t.tlbr for t in tracks]) without the per-track property calls (same arithmetic, same rounding)."""
+    out = np.empty((len(tracks), 4))
+    kf = [i for i, t in enumerate(tracks) if t.mean is not None]
+    raw = [i for i, t in enumerate(tracks) if t.mean is None]
+    if kf:
+        r = np.stack([tracks[i].mean[:4] for i in kf])  # (cx, cy, a, h)
+        w = r[:, 2] * r[:, 3]
+        x, y = r[:, 0] - w / 2, r[:, 1] - r[:, 3] / 2
+        out[kf] = np.stack([x, y, w + x, r[:, 3] + y], 1)
+    if raw:
+        r = np.stack([tracks[i]._tlwh for i in raw])
+        out[raw] = np.concatenate([r[:, :2], r[:, 2:] + r[:, :2]], 1)
+    return out
+
+
 def iou_distance(a_tracks, b_tracks, device):
     if not a_tracks or not b_tracks:
         return np.zeros((len(a_tracks), len(b_tracks)))
     with torch.cuda.stream(assoc_stream(device)):  # not behind the next frame's kernels on the main stream
-        a = torch.tensor(np.stack([t.tlbr for t in a_tracks]), dtype=torch.float32, device=device)
-        b = torch.tensor(np.stack([t.tlbr for t in b_tracks]), dtype=torch.float32, device=device)
+        a = torch.tensor(_tlbr_all(a_tracks), dtype=torch.float32, device=device)
+        b = torch.tensor(_tlbr_all(b_tracks), dtype=torch.float32, device=device)
         return 1.0 - ops.box_iou(a, b, plus_one=True).cpu().numpy().astype(np.float64)
 
 
@@ -174,7 +216,9 @@ class BYTETracker:
         boxes = boxes / min(img_size[0] / float(img_info[0]), img_size[1] / float(img_info[1]))
         hi = scores > self.args.track_thresh
         lo = (scores > 0.1) & (scores < self.args.track_thresh)
-        mk = lambda bs, ss: [STrack(np.r_[b[:2], b[2:] - b[:2]], s) for b, s in zip(bs, ss)]  # noqa: E731
+        def mk(bs, ss):  # tlbr -> tlwh for all detections at once
+            tlwh = np.concatenate([bs[:, :2], bs[:, 2:] - bs[:, :2]], 1)
+            return [STrack(t, s) for t, s in zip(tlwh, ss)]
         dets, dets2 = mk(boxes[hi], scores[hi]), mk(boxes[lo], scores[lo])
         activated, refound, lost, removed = [], [], [], []
         unconfirmed = [t for t in self.tracked if not t.is_activated]
@@ -186,21 +230,15 @@ class BYTETracker:
         if not getattr(self.args, "mot20", False):
             d = fuse_score(d, dets)
         m, u_trk, u_det = linear_assignment(d, self.args.match_thresh)
-        for it, idt in m:
-            t = pool[it]
-            if t.state == TRACKED:
-                t.update(dets[idt], self.frame_id); activated.append(t)
-            else:
-                t.update(dets[idt], self.frame_id, reactivate=True); refound.append(t)
+        for it, _ in m:
+            (activated if pool[it].state == TRACKED else refound).append(pool[it])
+        _update_matched([(pool[it], dets[idt]) for it, idt in m], self.frame_id)
         # second association: low-score detections against the still-tracked leftovers, plain IoU
         rest = [pool[i] for i in u_trk if pool[i].state == TRACKED]
         m, u_trk2, _ = linear_assignment(iou_distance(rest, dets2, self.device), 0.5)
-        for it, idt in m:
-            t = rest[it]
-            if t.state == TRACKED:
-                t.update(dets2[idt], self.frame_id); activated.append(t)
-            else:
-                t.update(dets2[idt], self.frame_id, reactivate=True); refound.append(t)
+        for it, _ in m:
+            (activated if rest[it].state == TRACKED else refound).append(rest[it])
+        _update_matched([(rest[it], dets2[idt]) for it, idt in m], self.frame_id)
         for it in u_trk2:
             if rest[it].state != LOST:
                 rest[it].state = LOST; lost.append(rest[it])
@@ -210,8 +248,8 @@ class BYTETracker:
         if not getattr(self.args, "mot20", False):
             d = fuse_score(d, dets_left)
         m, u_unc, u_det = linear_assignment(d, 0.7)
-        for it, idt in m:
-            unconfirmed[it].update(dets_left[idt], self.frame_id); activated.append(unconfirmed[it])
+        activated.extend(unconfirmed[it] for it, _ in m)
+        _update_matched([(unconfirmed[it], dets_left[idt]) for it, idt in m], self.frame_id)
         for it in u_unc:
             unconfirmed[it].state = REMOVED; removed.append(unconfirmed[it])
         for i in u_det:  # new tracks
