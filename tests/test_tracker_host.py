@@ -38,3 +38,27 @@ def test_byte_tracker_host_logic_matches_reference_golden(monkeypatch):
         assert rows.shape == ref.shape and np.array_equal(rows[:, 0], ref[:, 0]), (i, rows[:, 0], ref[:, 0])
         assert np.allclose(rows[:, 1:], ref[:, 1:], rtol=1e-4, atol=1e-2)
     assert bt.STrack._count == int(g["total_ids"])
+
+
+def test_qd_tracker_host_logic_matches_reference_golden(monkeypatch):
+    """QuasiDenseEmbedTracker.match / memo on CPU with numpy stand-ins for the two association kernels: the ids must
+    bit-match the reference class's over the 25-frame golden sequence (tests/golden/qd_tracker.npz)."""
+    import unicorn_b200.tracker.quasi_dense as qd
+    from unicorn_b200.synthetic import make_detections
+
+    def bisoftmax(e, m, ld=None, lm=None):
+        f = e @ m.t()
+        s = (f.softmax(1) + f.softmax(0)) / 2
+        return s * (ld[:, None] == lm[None, :]).float() if ld is not None else s
+
+    monkeypatch.setattr(qd.ops, "box_iou", lambda a, b, plus_one=False: _iou_np(a, b, plus_one))
+    monkeypatch.setattr(qd.ops, "bisoftmax", bisoftmax)
+    monkeypatch.setattr(qd, "assoc_stream", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    g = np.load(os.path.join(ROOT, "tests", "golden", "qd_tracker.npz"))
+    trk = qd.QuasiDenseEmbedTracker(device="cpu")
+    for i, (boxes, feats) in enumerate(make_detections(int(g["n_frames"]), int(g["n_obj"]), int(g["seed"]))):
+        b, _, ids = trk.match(boxes, torch.ones(boxes.size(0)), feats, i + 1)
+        assert np.array_equal(ids.numpy(), g[f"ids_{i}"]), (i, ids, g[f"ids_{i}"])
+        assert np.allclose(b.numpy(), g[f"boxes_{i}"])
+    assert trk.num_tracklets == int(g["num_tracklets"])
