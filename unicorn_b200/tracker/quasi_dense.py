@@ -101,20 +101,24 @@ class QuasiDenseEmbedTracker:
         if self.t_emb is None:
             self.t_emb = torch.zeros(0, embeds.size(1))
         pos = {int(t): k for k, t in enumerate(self.t_ids.tolist())}
-        add = []
+        add, rows, slots = [], [], []
         for r, tid in enumerate(ids.tolist()):
             if tid < 0:
                 continue
             k = pos.get(tid)
             if k is None:
                 add.append(r)
-                continue
-            vel = (bboxes[r] - self.t_box[k]) / float(frame_id - int(self.t_last[k]))
+            else:
+                rows.append(r)
+                slots.append(k)
+        if rows:  # every id occurs once per frame: the memo rows are updated together (same arithmetic as the per-track loop)
+            r, k = torch.tensor(rows, dtype=torch.long), torch.tensor(slots, dtype=torch.long)
+            vel = (bboxes[r] - self.t_box[k]) / (frame_id - self.t_last[k]).float()[:, None]
             self.t_box[k] = bboxes[r]
             self.t_emb[k] = (1 - self.memo_momentum) * self.t_emb[k] + self.memo_momentum * embeds[r]
             self.t_last[k] = frame_id
             self.t_lab[k] = labels[r]
-            acc = float(self.t_acc[k])
+            acc = self.t_acc[k].float()[:, None]
             self.t_vel[k] = (self.t_vel[k] * acc + vel) / (acc + 1)
             self.t_acc[k] += 1
         if add:
