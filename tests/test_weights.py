@@ -32,3 +32,27 @@ def test_seeded_weights_are_deterministic_and_perturbed():
     assert not torch.equal(a[k], c[k])
     assert a[k].abs().max() > 0  # zero-init in the reference (ms_deform_attn.py:63): perturbed so MSDA depends on data
     assert a["head.obj_preds_sot.0.bias"].mean() > -6
+
+
+def test_load_checkpoint_formats_and_validation(tmp_path):
+    """The reference checkpoint layout ({"model": state_dict}, optional DDP `module.` prefix, fp16 tensors) is accepted and
+    validated against the parameter table; wrong shapes / missing keys fail loudly."""
+    import pytest
+    from unicorn_b200.weights import check_state_dict, load_checkpoint
+    name = "unicorn_track_tiny"
+    sd = make_state_dict(name, 0)
+    p = tmp_path / "best_ckpt.pth"
+    torch.save({"model": {"module." + k: v.half() for k, v in sd.items()}, "start_epoch": 3}, p)
+    got = load_checkpoint(str(p), name)
+    assert list(got) == list(sd) and all(v.dtype == torch.float32 for v in got.values())
+    assert torch.equal(got["backbone.backbone.stages.0.0.gamma"], sd["backbone.backbone.stages.0.0.gamma"].half().float())
+    assert list(load_checkpoint(sd, name)) == list(sd)                     # bare state_dict
+    bad = dict(sd)
+    k0 = "backbone.backbone.stages.1.0.pwconv1.weight"
+    bad[k0] = bad[k0][:-1]
+    del bad["head.stems.0.conv.weight"]
+    bad["extra.weight"] = torch.zeros(1)
+    with pytest.raises(ValueError, match="does not match"):
+        load_checkpoint(bad, name)
+    missing, unexpected, mismatched = check_state_dict(bad, name, strict=False)
+    assert missing == ["head.stems.0.conv.weight"] and unexpected == ["extra.weight"] and mismatched[0][0] == k0

@@ -169,3 +169,34 @@ def make_state_dict(cfg_name, seed=0):
             t = n(*shape) / math.sqrt(fan_in)
         sd[name] = t.float().contiguous()
     return sd
+
+
+def check_state_dict(state_dict, cfg_name, strict=True):
+    """Compare a reference state_dict with the parameter table of `cfg_name`.  Returns (missing, unexpected, mismatched);
+    strict=True raises a ValueError that lists them (the engine would otherwise fail later with a KeyError deep inside
+    the weight packing).  Buffers the engine does not read (`head.mask_head.*`, BatchNorm `num_batches_tracked`) are ignored."""
+    want = param_shapes(cfg_name)
+    ignore = ("head.mask_head.", "num_batches_tracked")
+    have = {k: tuple(v.shape) for k, v in state_dict.items() if not any(s in k for s in ignore)}
+    missing = [k for k in want if k not in have]
+    unexpected = [k for k in have if k not in want]
+    mismatched = [(k, have[k], tuple(want[k])) for k in want if k in have and have[k] != tuple(want[k])]
+    if strict and (missing or unexpected or mismatched):
+        raise ValueError(f"state_dict does not match {cfg_name}: {len(missing)} missing (e.g. {missing[:3]}), "
+                         f"{len(unexpected)} unexpected (e.g. {unexpected[:3]}), {len(mismatched)} shape mismatches (e.g. {mismatched[:3]})")
+    return missing, unexpected, mismatched
+
+
+def load_checkpoint(path_or_obj, cfg_name, strict=True):
+    """The reference's checkpoint format (tools/track.py / unicorn/core/launch: torch.save({"model": state_dict, ...})): accepts the
+    file path or the loaded object, a bare state_dict, and DistributedDataParallel's `module.` prefix; returns an fp32 CPU
+    state_dict validated against the model's parameter table (ready for UnicornEngine / UnicornB200Model)."""
+    obj = torch.load(path_or_obj, map_location="cpu", weights_only=False) if isinstance(path_or_obj, (str, bytes)) or hasattr(path_or_obj, "read") else path_or_obj
+    sd = obj["model"] if isinstance(obj, dict) and "model" in obj and isinstance(obj["model"], dict) else obj
+    out = OrderedDict()
+    for k, v in sd.items():
+        if not torch.is_tensor(v):
+            continue
+        out[k[7:] if k.startswith("module.") else k] = v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.detach().cpu()
+    check_state_dict(out, cfg_name, strict=strict)
+    return out
