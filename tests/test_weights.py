@@ -47,6 +47,9 @@ def test_load_checkpoint_formats_and_validation(tmp_path):
     assert list(got) == list(sd) and all(v.dtype == torch.float32 for v in got.values())
     assert torch.equal(got["backbone.backbone.stages.0.0.gamma"], sd["backbone.backbone.stages.0.0.gamma"].half().float())
     assert list(load_checkpoint(sd, name)) == list(sd)                     # bare state_dict
+    m = make_state_dict("unicorn_track_tiny_mask", 0)                      # mask models: head.mask_head.* buffers are not parameters
+    assert len(load_checkpoint(m, "unicorn_track_tiny_mask")) == len(m)
+    assert len(load_checkpoint({k: v for k, v in m.items() if "mask_head" not in k}, "unicorn_track_tiny_mask")) == len(m) - 2
     bad = dict(sd)
     k0 = "backbone.backbone.stages.1.0.pwconv1.weight"
     bad[k0] = bad[k0][:-1]

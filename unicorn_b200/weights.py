@@ -175,8 +175,8 @@ def check_state_dict(state_dict, cfg_name, strict=True):
     """Compare a reference state_dict with the parameter table of `cfg_name`.  Returns (missing, unexpected, mismatched);
     strict=True raises a ValueError that lists them (the engine would otherwise fail later with a KeyError deep inside
     the weight packing).  Buffers the engine does not read (`head.mask_head.*`, BatchNorm `num_batches_tracked`) are ignored."""
-    want = param_shapes(cfg_name)
     ignore = ("head.mask_head.", "num_batches_tracked")
+    want = {k: v for k, v in param_shapes(cfg_name).items() if not any(s in k for s in ignore)}
     have = {k: tuple(v.shape) for k, v in state_dict.items() if not any(s in k for s in ignore)}
     missing = [k for k in want if k not in have]
     unexpected = [k for k in have if k not in want]
