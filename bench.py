@@ -175,7 +175,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from unicorn_b200 import _lib, ops
+    from unicorn_b200 import ops
     from unicorn_b200.engine import UnicornEngine
     from unicorn_b200.sot import UnicornSOTTrack
     from unicorn_b200.synthetic import make_video

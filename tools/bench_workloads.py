@@ -6,7 +6,6 @@
 Eager launches (no CUDA graph: the association step returns to the host every frame), wall clock around synchronised
 steps, synthetic video, seeded weights.  usage: bench_workloads.py mot|vos [frames]"""
 import json, os, sys, time, types
-import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

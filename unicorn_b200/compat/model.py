@@ -17,7 +17,6 @@ numbers).  `seq_dict` holds plain tensors (keys feat, pos, h, w) and survives co
 fused fast paths (correlation without the N x N matrix, CUDA-graph frames) live in the driver classes
 (unicorn_b200.sot / mot / vos), which is where a per-frame loop should go; this class is the drop-in for code that calls
 the model stage by stage.  There is no CPU path: tensors must be CUDA tensors on the engine's device."""
-import torch
 
 from .. import ops
 from ..engine import UnicornEngine

@@ -5,7 +5,6 @@ get_label_map :128-139) with the same initialize/track protocol (external/lib/te
 What changes relative to the reference loop: the reference frame's projection is cached, the whole steady-state
 frame (backbone -> interaction -> 2x upsample -> fused correlation -> head -> NMS) is one CUDA graph replay, and the
 only per-frame host traffic is the input frame (pinned H2D) and the top-`max_inst` detection rows (D2H)."""
-import numpy as np
 import torch
 
 from . import ops

@@ -2,7 +2,6 @@
 get_mask_results :129-155, get_det_results :157-201) for objects given in the first frame: one backbone pass and one
 fused correlation per frame (all objects' label maps are propagated by a single uc_corr_propagate launch, n_obj <= 8),
 then per object: prior pyramid -> mask head -> NMS -> dynamic-conv mask of the best instance."""
-import numpy as np
 import torch
 
 from . import ops
