@@ -49,3 +49,34 @@ def test_rle_hand_example_and_round_trip():
         s = R.rle_encode(m)
         assert all(48 <= ord(c) < 112 for c in s)
         assert np.array_equal(R.rle_decode(s, *shape), m)
+
+
+def test_mots_frame_result_equals_reference_steps():
+    """mots_frame_result against the reference's per-frame steps written out literally (mot_evaluator.py:850-897: sort by id,
+    overlap-free loop, min_box_area filter, RLE of the Fortran-ordered mask, 1-based ids)."""
+    g = torch.Generator().manual_seed(3)
+    n, H, W = 7, 48, 64
+    ids = torch.tensor([5, 2, 9, 0, 7, 3, 1])
+    boxes = torch.rand(n, 5, generator=g) * torch.tensor([30.0, 20.0, 40.0, 40.0, 1.0])
+    boxes[:, 2:4] += boxes[:, :2] + 15.0          # every box at least 15 x 15
+    boxes[3, 2:4] = boxes[3, :2] + 2.0            # area 4: filtered out by min_box_area
+    masks = torch.rand(n, H, W, generator=g) > 0.55
+    frame = R.mots_frame_result(11, boxes, ids, masks, 720, 1280, min_box_area=100)
+    # literal restatement
+    _, inds = ids.sort(descending=False)
+    s_ids, s_boxes, s_masks = ids[inds], boxes[inds], masks[inds]
+    new = s_masks.clone()
+    prev = s_masks[0].clone()
+    for k in range(1, n):
+        new[k] = torch.logical_and(torch.logical_not(prev), s_masks[k])
+        prev = torch.logical_or(prev, s_masks[k])
+    exp_ids, exp_rle = [], []
+    for i in range(n):
+        x1, y1, x2, y2, _ = s_boxes[i].tolist()
+        if (x2 - x1) * (y2 - y1) > 100:
+            exp_rle.append(R.rle_encode(np.asfortranarray(new[i].numpy())))
+            exp_ids.append(int(s_ids[i]) + 1)
+    assert frame == (11, exp_ids, 2, 720, 1280, exp_rle)
+    assert 1 not in frame[1] and len(frame[1]) == n - 1     # id 0 (+1) was the tiny box
+    for rle, i in zip(frame[5], [j for j in range(n) if j != 0]):
+        assert np.array_equal(R.rle_decode(rle, H, W), new[i].numpy())

@@ -100,3 +100,25 @@ def rle_decode(s, H, W):
         pos += c
         val = not val
     return flat.reshape(H, W, order="F")
+
+
+def mots_frame_result(frame_id, boxes, ids, masks, img_h, img_w, min_box_area=100, cat_id=2):
+    """Host half of one MOTS frame after association (mot_evaluator.py:846-897): boxes [n,5] (x1,y1,x2,y2,score) and ids [n]
+    as returned by QuasiDenseEmbedTracker.match (valid ids only, any order), masks bool [n,H,W] in the same order.
+    Sorts by ascending id, makes the masks overlap free in that order, drops boxes with area <= min_box_area, encodes the
+    survivors and returns the tuple write_results_mots() consumes: (frame_id, ids + 1, cat_id, img_h, img_w, rles)."""
+    ids = torch.as_tensor(ids).long()
+    boxes = torch.as_tensor(boxes, dtype=torch.float32)
+    order = ids.sort()[1]
+    ids, boxes, masks = ids[order], boxes[order], masks[order]
+    free = overlap_free(masks).cpu().numpy() if masks.size(0) else None
+    out_ids, rles = [], []
+    for i in range(boxes.size(0)):
+        tid = int(ids[i])
+        if tid < 0:
+            continue
+        x1, y1, x2, y2 = boxes[i, :4].tolist()
+        if (x2 - x1) * (y2 - y1) > min_box_area:
+            rles.append(rle_encode(free[i]))
+            out_ids.append(tid + 1)  # 1-based ids for the MOTS files
+    return frame_id, out_ids, cat_id, img_h, img_w, rles
