@@ -48,7 +48,7 @@ extern "C" {
 /* fused activations */
 #define UC_ACT_NONE 0
 #define UC_ACT_RELU 1
-#define UC_ACT_GELU 2 /* exact erf GELU (nn.GELU()) */
+#define UC_ACT_GELU 2 /* exact erf GELU (nn.GELU()), evaluated as x*sigmoid(x*P(x^2)), |error| < 4e-6 */
 #define UC_ACT_SILU 3
 #define UC_ACT_SIGMOID 4
 
@@ -62,7 +62,9 @@ UC_API int uc_check_device(void);
  *   w : packed weights [Cout][KH*KW][Cin] in the same 16-bit type as x (K-major)
  *   y : NHWC output, pixel stride ldy, dtype y_dtype; y = act(conv(x) + bias) ; then y = res + gamma * y if given
  * A Linear layer on [M, Cin] rows is B=1, H=1, W=M, KH=KW=1.  stride in {1,2}; pad < KH.
- * Cin % 8 == 0, Cout % 8 == 0 (pad the weight rows / output channels otherwise).
+ * Cin % 8 == 0, Cout % 8 == 0 (pad the weight rows / output channels otherwise).  Outputs (and residuals) whose rows start on
+ * 32-byte boundaries (ldy * sizeof % 32 == 0, y % 32 == 0) are written with one 256-bit store per 16 channels; other
+ * layouts fall back to 128-bit stores.  Every launch is CUDA-graph capturable and uses programmatic dependent launch.
  */
 typedef struct UcConv2d {
   const void* x;
@@ -95,7 +97,9 @@ UC_API int uc_conv2d(const UcConv2d* d, void* stream);
 UC_API int uc_stem_ln(const void* img, int img_is_u8_hwc, const float* w48, const float* bias, const float* lnw, const float* lnb,
                       void* out_bf16, int B, int H, int W, int C0, float eps, void* stream);
 
-/* ConvNeXt block front half: depthwise 7x7 (pad 3)+bias then LayerNorm over C (convnext.py:43-45).
+/* ConvNeXt block front half in ONE launch: depthwise 7x7 (pad 3)+bias then LayerNorm over C (convnext.py:43-45); the
+ * intermediate map stays in shared memory (C % 64 == 0; other C use a one-warp-row kernel).  Not in place.  The engine uses
+ * uc_dwconv7 + uc_layernorm instead, which is faster on ConvNeXt-L's shapes.
  * x,y NHWC bf16 contiguous [B,H,W,C]; w49 fp32 [49][C] (k = kh*7+kw). */
 UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias, const float* lnw, const float* lnb,
                          void* y_bf16, int B, int H, int W, int C, float eps, void* stream);
