@@ -59,3 +59,19 @@ def test_load_checkpoint_formats_and_validation(tmp_path):
         load_checkpoint(bad, name)
     missing, unexpected, mismatched = check_state_dict(bad, name, strict=False)
     assert missing == ["head.stems.0.conv.weight"] and unexpected == ["extra.weight"] and mismatched[0][0] == k0
+
+
+def test_committed_tuning_tables_are_well_formed():
+    """unicorn_b200/tuned/*.json: layer-shape keys (12 '|'-separated fields) -> an N tile the C side accepts."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "unicorn_b200", "tuned", "*.json"))
+    assert files
+    valid = {0, 16, 32, 64, 96, 128, 192, 256, 1128, 1192, 1256}
+    for f in files:
+        tab = json.load(open(f))
+        assert tab, f
+        for k, v in tab.items():
+            assert len(k.split("|")) == 12 and v in valid, (f, k, v)
