@@ -26,6 +26,8 @@ constexpr int kMaxTaps = 9;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kConvEpiWarps = 16;                       // four per TMEM lane quadrant
 constexpr int kConvThreads = (2 + kConvEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, then the epilogue warps
+constexpr int kGnMaxLocal = 64;                         // GroupNorm groups per N tile (tile width 256 / group size >= 4)
+constexpr int kGnSmemBytes = 2 * kGnMaxLocal * 2 * 8;   // two tile parities x {sum, sumsq} int64
 
 struct ConvTap {
   int16_t map, dw, dh, tap;
@@ -104,10 +106,11 @@ __device__ __forceinline__ uint32_t pack2_fast(float lo, float hi, bool f16) {  
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// GroupNorm partial sums of one epilogue item (this warp's 32 rows x ncols columns starting at channel cbase).  A group
-// may straddle items / warps / CTAs: partial sums are simply added by the order-independent fixed-point atomics.
+// GroupNorm partial sums of one epilogue item (this warp's 32 rows x ncols columns starting at channel cbase), added to the
+// CTA's shared-memory accumulators of the current tile (fixed point, integer adds: order independent).  g0 = first group of
+// the N tile (an N tile never splits a group).
 __device__ __forceinline__ void gn_partial_sums(const float (&f)[16], const ConvKernelParams& p, int cbase, int ncols, bool valid,
-                                             int b, int lane, bool tile_ok) {
+                                             int lane, unsigned long long* acc_tile, int g0) {
   int c = 0;
 #pragma unroll 1
   while (c < ncols) {
@@ -125,10 +128,9 @@ __device__ __forceinline__ void gn_partial_sums(const float (&f)[16], const Conv
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0 && tile_ok) {
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + g) * 2;
-      atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
-      atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
+    if (lane == 0) {
+      atomicAdd(acc_tile + (g - g0) * 2, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+      atomicAdd(acc_tile + (g - g0) * 2 + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
     }
     c = end;
   }
@@ -157,6 +159,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // per-CTA GroupNorm accumulators (fixed point): the epilogue warps add into shared memory, ONE global atomic per group and
+  // tile follows — the short-K GN convs were bound by ~36k global atomics on the 32 addresses of an image
+  unsigned long long* gn_acc = reinterpret_cast<unsigned long long*>(smem + STAGES * (kABytes + B_BYTES) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kiters = p.ntaps * p.kchunks;
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 2 * kGnMaxLocal * 2; i += kConvThreads) gn_acc[i] = 0ull;
   if (warp == 1) {
     if (CLUSTER > 1) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     const int wi = row % p.tile_w, hi = row / p.tile_w;
     const bool f16 = p.y_dtype == UC_F16;
     constexpr int ROUNDS = (BLOCK_N + 63) / 64;
-    int acc = 0, acc_phase = 0;
+    int acc = 0, acc_phase = 0, gpar = 0;
     for (int item = item0; item < num_items; item += item_step) {
       const int n0 = (item % p.n_tiles) * BLOCK_N;
       const int mt = (item / p.n_tiles) * CLUSTER + crank;
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           float f[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { f[2 * j] = lo2(h[j]); f[2 * j + 1] = hi2(h[j]); }
-          if (p.gn_stats) gn_partial_sums(f, p, cbase, ncols, valid, b, lane, tile_ok);
+          if (p.gn_stats) gn_partial_sums(f, p, cbase, ncols, valid, lane, gn_acc + gpar * (kGnMaxLocal * 2), n0 / p.gn_gs);
           switch (p.act) {
             case UC_ACT_RELU:
 #pragma unroll
@@ -421,6 +427,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           else mbar_arrive(&tmem_empty[acc]);
         }
       }
+      if (p.gn_stats) {
+        // every epilogue warp has added its partial sums of this tile: one global atomic per group, then the slots are
+        // cleared for the tile after next (the next tile uses the other parity, so no second barrier is needed)
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
+        const int et = static_cast<int>(threadIdx.x) - 64;  // 0 .. 511 over the epilogue warps
+        const int ng = (limit + p.gn_gs - 1) / p.gn_gs;
+        if (et < 2 * ng) {
+          unsigned long long* slot = gn_acc + gpar * (kGnMaxLocal * 2) + et;
+          const unsigned long long v = *slot;
+          *slot = 0ull;
+          if (tile_ok && v != 0ull) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) +
+                                      (static_cast<size_t>(b) * p.gn_groups + n0 / p.gn_gs) * 2 + et;
+            atomicAdd(dst, v);
+          }
+        }
+        gpar ^= 1;
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -439,7 +463,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 
 template <int BLOCK_N, int STAGES, int CLUSTER>
 static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256 + kGnSmemBytes;
   static int per_sm = 0;
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>;
   if (!per_sm) {
