@@ -51,6 +51,9 @@ struct alignas(64) ConvKernelParams {
   int ldy, y_dtype, act;
   int wide_store, wide_res;
   int debug;  // tools only (UC_CONV_DEBUG): 1 = no MMA (operand feed rate alone), 2 = no TMA loads (MMA + epilogue alone)  // 256-bit stores / residual loads possible (32-byte aligned rows)
+  const long long* row_stats;  // LayerNorm folded into this 1x1 conv: per input pixel {sum, sumsq} (fixed point 2^22) ...
+  const float* col_s;          // ... column sums of the folded weights, channel count and epsilon of the LayerNorm
+  float row_c, row_eps;
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -298,6 +301,16 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && tile_ok;
       const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
       const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
+      // LayerNorm folded into the GEMM: y = rstd * (W' x) - rstd * mu * colsum(W') + c ; (mu, rstd) of this lane's pixel
+      float r_rstd = 1.f, r_murstd = 0.f;
+      if (p.row_stats && valid) {
+        const long long* st = p.row_stats + pix * 2;
+        const double inv = 1.0 / (static_cast<double>(kGnFixedScale) * p.row_c);
+        const double mu = static_cast<double>(st[0]) * inv;
+        const float var = fmaxf(static_cast<float>(static_cast<double>(st[1]) * inv - mu * mu), 0.f);
+        r_rstd = rsqrtf(var + p.row_eps);
+        r_murstd = static_cast<float>(mu) * r_rstd;
+      }
       // this warp's last round with columns to read: the accumulator is handed back to the MMA warp right after it
       const int last_rd = (limit - 1 - cg * 16) >= 0 ? min(ROUNDS - 1, (limit - 1 - cg * 16) / 64) : -1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -343,10 +356,20 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           }
         }
         f32x2 h[8];
+        if (p.row_stats) {
+          const f32x2 rs = pk2(r_rstd, r_rstd), nm = pk2(-r_murstd, -r_murstd);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          h[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb[j].x, bb[j].y));
-          h[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb[j].z, bb[j].w));
+          for (int j = 0; j < 4; ++j) {
+            const float4 cs = (4 * j < ncols) ? __ldg(reinterpret_cast<const float4*>(p.col_s + cbase) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            h[2 * j] = fma2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), rs, fma2(nm, pk2(cs.x, cs.y), pk2(bb[j].x, bb[j].y)));
+            h[2 * j + 1] = fma2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), rs, fma2(nm, pk2(cs.z, cs.w), pk2(bb[j].z, bb[j].w)));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb[j].x, bb[j].y));
+            h[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb[j].z, bb[j].w));
+          }
         }
         if (p.act == UC_ACT_GELU && !p.gn_stats) {
 #pragma unroll
@@ -633,6 +656,9 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res; p.ldres = d->ldres;
   p.y = d->y; p.ldy = d->ldy; p.y_dtype = d->y_dtype; p.act = d->act;
+  p.row_stats = static_cast<const long long*>(d->row_stats); p.col_s = d->col_s; p.row_c = static_cast<float>(d->Cin); p.row_eps = d->row_eps;
+  if (d->row_stats && (!d->col_s || d->KH != 1 || d->KW != 1 || d->stride != 1 || d->pad != 0))
+    return set_error(UC_EINVAL, "uc_conv2d: row_stats (folded LayerNorm) needs a 1x1 stride-1 conv and col_s");
   p.gn_stats = static_cast<long long*>(d->gn_stats); p.gn_groups = d->gn_groups;
   p.gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 1 << 30;
   if (d->gn_stats && (bn % p.gn_gs) != 0)
