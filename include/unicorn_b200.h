@@ -87,6 +87,12 @@ typedef struct UcConv2d {
    * bit-reproducible); must be zeroed by the caller; NULL = off.  Consumed by uc_groupnorm_apply. */
   void* gn_stats;
   int gn_groups;
+  /* Optional LayerNorm folded into a 1x1 conv (ConvNeXt block, convnext.py:45-46): x is the UN-normalised map, w = W * diag(ln_w),
+   * bias = W @ ln_b + b, col_s[n] = sum_k w[n][k] (of the 16-bit weights), row_stats = per-pixel {sum, sumsq} over Cin of x as
+   * written by uc_dwconv7 (int64 fixed point 2^22): y = act(rstd * (w x) - rstd * mu * col_s + bias).  NULL = off. */
+  const void* row_stats;
+  const float* col_s;
+  float row_eps;
 } UcConv2d;
 UC_API int uc_conv2d(const UcConv2d* d, void* stream);
 
@@ -105,8 +111,10 @@ UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias
                          void* y_bf16, int B, int H, int W, int C, float eps, void* stream);
 
 /* Depthwise 7x7 (pad 3)+bias only (shared-memory tiled); follow with uc_layernorm for the ConvNeXt block. */
+/* ln_stats (optional, may be NULL): [B*H*W][2] int64 fixed point (value * 2^22), zeroed by the caller; receives the per-pixel
+ * {sum, sum of squares} over C of the stored outputs, for a pwconv1 with the LayerNorm folded in (UcConv2d.row_stats). */
 UC_API int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
-                      void* stream);
+                      void* ln_stats, void* stream);
 
 /* Row LayerNorm: y[m,:] = LN(x[m,:] + res[m,:]) * w + b  (res may be NULL).  16-bit rows with element strides.
  * convnext.py:176-184 (downsample / out norms), deformable_transformer.py:113,121,127-130 (post-norm). */

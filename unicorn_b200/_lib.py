@@ -24,6 +24,7 @@ class UcConv2d(ctypes.Structure):
         ("y", ctypes.c_void_p), ("ldy", ctypes.c_int), ("y_dtype", ctypes.c_int),
         ("block_n", ctypes.c_int),
         ("gn_stats", ctypes.c_void_p), ("gn_groups", ctypes.c_int),
+        ("row_stats", ctypes.c_void_p), ("col_s", ctypes.c_void_p), ("row_eps", ctypes.c_float),
     ]
 
 

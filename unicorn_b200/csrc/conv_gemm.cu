@@ -26,6 +26,8 @@ constexpr int kMaxTaps = 9;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kConvEpiWarps = 16;                       // four per TMEM lane quadrant
 constexpr int kConvThreads = (2 + kConvEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, then the epilogue warps
+constexpr int kGnMaxLocal = 64;                         // GroupNorm groups per N tile (tile width 256 / group size >= 4)
+constexpr int kGnSmemBytes = 2 * kGnMaxLocal * 2 * 8;   // two tile parities x {sum, sumsq} int64
 
 struct ConvTap {
   int16_t map, dw, dh, tap;
@@ -49,6 +51,9 @@ struct alignas(64) ConvKernelParams {
   int ldy, y_dtype, act;
   int wide_store, wide_res;
   int debug;  // tools only (UC_CONV_DEBUG): 1 = no MMA (operand feed rate alone), 2 = no TMA loads (MMA + epilogue alone)  // 256-bit stores / residual loads possible (32-byte aligned rows)
+  const long long* row_stats;  // LayerNorm folded into this 1x1 conv: per input pixel {sum, sumsq} (fixed point 2^22) ...
+  const float* col_s;          // ... column sums of the folded weights, channel count and epsilon of the LayerNorm
+  float row_c, row_eps;
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -104,10 +109,11 @@ __device__ __forceinline__ uint32_t pack2_fast(float lo, float hi, bool f16) {  
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// GroupNorm partial sums of one epilogue item (this warp's 32 rows x ncols columns starting at channel cbase).  A group
-// may straddle items / warps / CTAs: partial sums are simply added by the order-independent fixed-point atomics.
+// GroupNorm partial sums of one epilogue item (this warp's 32 rows x ncols columns starting at channel cbase), added to the
+// CTA's shared-memory accumulators of the current tile (fixed point, integer adds: order independent).  g0 = first group of
+// the N tile (an N tile never splits a group).
 __device__ __forceinline__ void gn_partial_sums(const float (&f)[16], const ConvKernelParams& p, int cbase, int ncols, bool valid,
-                                             int b, int lane, bool tile_ok) {
+                                             int lane, unsigned long long* acc_tile, int g0) {
   int c = 0;
 #pragma unroll 1
   while (c < ncols) {
@@ -125,10 +131,9 @@ __device__ __forceinline__ void gn_partial_sums(const float (&f)[16], const Conv
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0 && tile_ok) {
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + g) * 2;
-      atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
-      atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
+    if (lane == 0) {
+      atomicAdd(acc_tile + (g - g0) * 2, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+      atomicAdd(acc_tile + (g - g0) * 2 + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
     }
     c = end;
   }
@@ -157,6 +162,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // per-CTA GroupNorm accumulators (fixed point): the epilogue warps add into shared memory, ONE global atomic per group and
+  // tile follows — the short-K GN convs were bound by ~36k global atomics on the 32 addresses of an image
+  unsigned long long* gn_acc = reinterpret_cast<unsigned long long*>(smem + STAGES * (kABytes + B_BYTES) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kiters = p.ntaps * p.kchunks;
@@ -178,6 +186,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 2 * kGnMaxLocal * 2; i += kConvThreads) gn_acc[i] = 0ull;
   if (warp == 1) {
     if (CLUSTER > 1) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
     const int wi = row % p.tile_w, hi = row / p.tile_w;
     const bool f16 = p.y_dtype == UC_F16;
     constexpr int ROUNDS = (BLOCK_N + 63) / 64;
-    int acc = 0, acc_phase = 0;
+    int acc = 0, acc_phase = 0, gpar = 0;
     for (int item = item0; item < num_items; item += item_step) {
       const int n0 = (item % p.n_tiles) * BLOCK_N;
       const int mt = (item / p.n_tiles) * CLUSTER + crank;
@@ -292,6 +301,16 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && tile_ok;
       const size_t pix = (static_cast<size_t>(b) * p.Ho + oh) * p.Wo + ow;
       const int limit = min(BLOCK_N, p.Cout - n0);  // valid columns of this tile (multiple of 8)
+      // LayerNorm folded into the GEMM: y = rstd * (W' x) - rstd * mu * colsum(W') + c ; (mu, rstd) of this lane's pixel
+      float r_rstd = 1.f, r_murstd = 0.f;
+      if (p.row_stats && valid) {
+        const long long* st = p.row_stats + pix * 2;
+        const double inv = 1.0 / (static_cast<double>(kGnFixedScale) * p.row_c);
+        const double mu = static_cast<double>(st[0]) * inv;
+        const float var = fmaxf(static_cast<float>(static_cast<double>(st[1]) * inv - mu * mu), 0.f);
+        r_rstd = rsqrtf(var + p.row_eps);
+        r_murstd = static_cast<float>(mu) * r_rstd;
+      }
       // this warp's last round with columns to read: the accumulator is handed back to the MMA warp right after it
       const int last_rd = (limit - 1 - cg * 16) >= 0 ? min(ROUNDS - 1, (limit - 1 - cg * 16) / 64) : -1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -337,10 +356,20 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           }
         }
         f32x2 h[8];
+        if (p.row_stats) {
+          const f32x2 rs = pk2(r_rstd, r_rstd), nm = pk2(-r_murstd, -r_murstd);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          h[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb[j].x, bb[j].y));
-          h[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb[j].z, bb[j].w));
+          for (int j = 0; j < 4; ++j) {
+            const float4 cs = (4 * j < ncols) ? __ldg(reinterpret_cast<const float4*>(p.col_s + cbase) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            h[2 * j] = fma2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), rs, fma2(nm, pk2(cs.x, cs.y), pk2(bb[j].x, bb[j].y)));
+            h[2 * j + 1] = fma2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), rs, fma2(nm, pk2(cs.z, cs.w), pk2(bb[j].z, bb[j].w)));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb[j].x, bb[j].y));
+            h[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb[j].z, bb[j].w));
+          }
         }
         if (p.act == UC_ACT_GELU && !p.gn_stats) {
 #pragma unroll
@@ -349,7 +378,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           float f[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { f[2 * j] = lo2(h[j]); f[2 * j + 1] = hi2(h[j]); }
-          if (p.gn_stats) gn_partial_sums(f, p, cbase, ncols, valid, b, lane, tile_ok);
+          if (p.gn_stats) gn_partial_sums(f, p, cbase, ncols, valid, lane, gn_acc + gpar * (kGnMaxLocal * 2), n0 / p.gn_gs);
           switch (p.act) {
             case UC_ACT_RELU:
 #pragma unroll
@@ -421,6 +450,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
           else mbar_arrive(&tmem_empty[acc]);
         }
       }
+      if (p.gn_stats) {
+        // every epilogue warp has added its partial sums of this tile: one global atomic per group, then the slots are
+        // cleared for the tile after next (the next tile uses the other parity, so no second barrier is needed)
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
+        const int et = static_cast<int>(threadIdx.x) - 64;  // 0 .. 511 over the epilogue warps
+        const int ng = (limit + p.gn_gs - 1) / p.gn_gs;
+        if (et < 2 * ng) {
+          unsigned long long* slot = gn_acc + gpar * (kGnMaxLocal * 2) + et;
+          const unsigned long long v = *slot;
+          *slot = 0ull;
+          if (tile_ok && v != 0ull) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_stats) +
+                                      (static_cast<size_t>(b) * p.gn_groups + n0 / p.gn_gs) * 2 + et;
+            atomicAdd(dst, v);
+          }
+        }
+        gpar ^= 1;
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -439,7 +486,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 
 template <int BLOCK_N, int STAGES, int CLUSTER>
 static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256 + kGnSmemBytes;
   static int per_sm = 0;
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>;
   if (!per_sm) {
@@ -609,6 +656,9 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
   p.idesc = umma_idesc_f16(d->x_dtype == UC_BF16 ? 1u : 0u, kBlockM, static_cast<uint32_t>(bn));
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res; p.ldres = d->ldres;
   p.y = d->y; p.ldy = d->ldy; p.y_dtype = d->y_dtype; p.act = d->act;
+  p.row_stats = static_cast<const long long*>(d->row_stats); p.col_s = d->col_s; p.row_c = static_cast<float>(d->Cin); p.row_eps = d->row_eps;
+  if (d->row_stats && (!d->col_s || d->KH != 1 || d->KW != 1 || d->stride != 1 || d->pad != 0))
+    return set_error(UC_EINVAL, "uc_conv2d: row_stats (folded LayerNorm) needs a 1x1 stride-1 conv and col_s");
   p.gn_stats = static_cast<long long*>(d->gn_stats); p.gn_groups = d->gn_groups;
   p.gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 1 << 30;
   if (d->gn_stats && (bn % p.gn_gs) != 0)

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const uint32_t* __restr
 template <int CCH>
 __global__ void __launch_bounds__(512, 2) dwconv7_tiled_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, uint16_t* __restrict__ y, int H,
-                                                                int W, int C, int tiles_w) {
+                                                                int W, int C, int tiles_w, long long* __restrict__ ln_stats) {
   pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
   pdl_launch_dependents();  // ... and the next kernel in the stream may become resident / run its prologue from here on
   // 512 threads = (CCH/2 channel pairs) x (TH rows) x (2 half rows of 8 pixels): 16 accumulators + 14 staged inputs per
@@ -252,6 +252,28 @@ __global__ void __launch_bounds__(512, 2) dwconv7_tiled_kernel(const uint16_t* _
     a1[p] = __uint_as_float(static_cast<uint32_t>(acc[p] >> 32));
   }
   const int oh = oh0 + r;
+  if (ln_stats) {
+    // Per-pixel LayerNorm statistics of the STORED (bf16-rounded) values, summed over this CTA's CCH channels and added to
+    // [pixel]{sum, sumsq} in fixed point (order independent): the following pwconv1 applies the normalisation in its
+    // epilogue (LayerNorm folded into the GEMM), so the separate LayerNorm pass disappears.
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const uint32_t pk = pack_bf16(a0[p], a1[p]);
+      const float r0 = bf16lo(pk), r1 = bf16hi(pk);
+      float s1 = r0 + r1, s2 = fmaf(r0, r0, r1 * r1);
+#pragma unroll
+      for (int o = PAIRS / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const int ow = ow0 + hx * PX + p;
+      if (cp == 0 && oh < H && ow < W) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(ln_stats) + ((static_cast<long>(b) * H + oh) * W + ow) * 2;
+        atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s1 * kGnFixedScale)));
+        atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kGnFixedScale)));
+      }
+    }
+  }
   if (oh < H) {
     uint32_t* yr = reinterpret_cast<uint32_t*>(y + (static_cast<long>(b) * H + oh) * W * C + c0) + cp;
 #pragma unroll
@@ -661,7 +683,7 @@ extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* 
 }
 
 extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
-                          void* stream_v) {
+                          void* ln_stats, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!x_bf16 || !w49 || !bias || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7: null pointer");
   if (C % 32) return set_error(UC_EINVAL, "uc_dwconv7: C must be a multiple of 32");
@@ -671,11 +693,11 @@ extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bia
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(dwconv7_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     dim3 grid(tiles_w * ((H + 7) / 8), C / 64, B);
-    launch_pdl(dwconv7_tiled_kernel<64>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    launch_pdl(dwconv7_tiled_kernel<64>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w, static_cast<long long*>(ln_stats));
   } else {
     constexpr int smem = (16 + 6) * 22 * 64 + 49 * 32 * 4;
     dim3 grid(tiles_w * ((H + 15) / 16), C / 32, B);
-    launch_pdl(dwconv7_tiled_kernel<32>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w);
+    launch_pdl(dwconv7_tiled_kernel<32>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w, static_cast<long long*>(ln_stats));
   }
   return check_launch("uc_dwconv7");
 }

@@ -35,7 +35,7 @@ class _ConvGN:
 
 
 class UnicornEngine:
-    def __init__(self, state_dict, cfg_name, device="cuda", autotune=True):
+    def __init__(self, state_dict, cfg_name, device="cuda", autotune=True, ln_fold=None):
         ops._lib.check(ops._lib.lib().uc_check_device(), "uc_check_device")  # fail loudly without an sm_100 GPU
         self.cfg_name = cfg_name
         self.cfg = CONFIGS[cfg_name]
@@ -52,6 +52,10 @@ class UnicornEngine:
         self._with_masks = False
         self._bn_cache = {}
         self._bn_dirty = False
+        # ln_fold: the ConvNeXt blocks' LayerNorm is folded into pwconv1 (statistics from the depthwise kernel, normalisation in
+        # the GEMM epilogue) — UNTESTED on a GPU (round-2 item); off unless asked for / UC_LN_FOLD=1
+        self.ln_fold = bool(int(os.environ.get("UC_LN_FOLD", "0"))) if ln_fold is None else bool(ln_fold)
+        self._row_arena, self._row_used = None, 0
         self.autotune = autotune
         self.load_tuning()
         self._load(state_dict)
@@ -71,9 +75,15 @@ class UnicornEngine:
             P[f"outnorm{i}"] = (f(b + f"norm{i}.weight"), f(b + f"norm{i}.bias"))
 
         def block(p):
-            return dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
-                        lnb=f(p + "norm.bias"), w1=pw(p + "pwconv1.weight"), b1=f(p + "pwconv1.bias"), w2=pw(p + "pwconv2.weight"),
-                        b2=f(p + "pwconv2.bias"), gamma=f(p + "gamma"))
+            d = dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
+                     lnb=f(p + "norm.bias"), w1=pw(p + "pwconv1.weight"), b1=f(p + "pwconv1.bias"), w2=pw(p + "pwconv2.weight"),
+                     b2=f(p + "pwconv2.bias"), gamma=f(p + "gamma"))
+            if self.ln_fold:  # W' = W diag(g) (16-bit), colsum(W') of the ROUNDED weights, c = W beta + b
+                w1 = sd[p + "pwconv1.weight"].to(dev, F32).reshape(d["b1"].numel(), -1)
+                d["w1f"] = ops.pack_conv_weight((w1 * d["lnw"][None, :])[:, :, None, None])
+                d["s1"] = d["w1f"].float().sum(dim=(1, 2)).contiguous()
+                d["c1"] = (w1 @ d["lnb"] + d["b1"]).contiguous()
+            return d
 
         P["stages"] = [[block(b + f"stages.{i}.{j}.") for j in range(self.depths[i])] for i in range(4)]
 
@@ -152,7 +162,7 @@ class UnicornEngine:
         B, H, W, Cin = x.shape
         Cout = w.shape[0]
         gn = kw.get("gn_groups", 0)
-        key = (B, H, W, Cin, Cout, k, stride, pad, kw.get("act", 0), gn, kw.get("res") is not None, out.dtype)
+        key = (B, H, W, Cin, Cout, k, stride, pad, kw.get("act", 0), gn, kw.get("res") is not None, out.dtype) + (("lnfold",) if kw.get("row_stats") is not None else ())
         key = "|".join(str(v) for v in key)
         bn = self._bn_cache.get(key)
         if bn is None:
@@ -234,6 +244,20 @@ class UnicornEngine:
         else:
             self._stats_arena.zero_()
         self._stats_used = 0
+        if self._row_arena is not None:
+            self._row_arena.zero_()
+        self._row_used = 0
+
+    def _row_stats(self, n_pix):
+        """[n_pix, 2] int64 slice of the per-frame LayerNorm-statistics arena (zeroed by begin_frame, handed out in call order)."""
+        need = self._row_used + n_pix
+        if self._row_arena is None or need > self._row_arena.shape[0]:
+            assert not torch.cuda.is_current_stream_capturing(), "row-statistics arena must be sized by an eager frame first"
+            grown = torch.zeros(max(need, 2 * (0 if self._row_arena is None else self._row_arena.shape[0]), 1 << 16), 2, dtype=torch.int64, device=self.dev)
+            self._row_arena = grown  # earlier slices of this frame stay alive through the tensors that reference the old arena
+        s = self._row_arena[self._row_used:need]
+        self._row_used = need
+        return s
 
     def _stats(self, groups):
         s = self._stats_arena[self._stats_used]
@@ -255,6 +279,13 @@ class UnicornEngine:
         # two launches: the channel-chunked tiled depthwise kernel + a row LayerNorm on the L2-resident result.  The fused
         # one-CTA-per-pixel-tile kernel (ops.dwconv7_ln) was measured slower on every stage of ConvNeXt-L (34.6 vs 28 us on
         # stage 3: 2.3x the instructions per output, 8 warps per SM) — see DESIGN.md 4.3.
+        if self.ln_fold and C % 32 == 0:
+            rs = self._row_stats(B * H * W)
+            t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), ln_stats=rs)
+            hid = self.conv(t, bp["w1f"], 1, bias=bp["c1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)),
+                            row_stats=rs, col_s=bp["s1"], row_eps=1e-6)
+            self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
+            return x
         t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape))
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
         hid = self.conv(t, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))

@@ -45,7 +45,7 @@ CONV_TRACE = None
 
 
 def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=None, res=None, out=None,
-           out_dtype=None, block_n=0, gn_stats=None, gn_groups=0):
+           out_dtype=None, block_n=0, gn_stats=None, gn_groups=0, row_stats=None, col_s=None, row_eps=1e-6):
     """x: NHWC view (B,H,W,Cin) bf16/f16.  w_packed: [Cout, KH*KW, Cin].  Returns NHWC (B,Ho,Wo,Cout)."""
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
@@ -72,6 +72,9 @@ def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=
     d.y, d.ldy, d.y_dtype = _p(out), _nhwc_ld(out), _DT[out.dtype]
     d.block_n = block_n
     d.gn_stats, d.gn_groups = _p(gn_stats), gn_groups
+    d.row_stats, d.col_s, d.row_eps = _p(row_stats), _p(col_s), row_eps
+    if row_stats is not None:
+        assert row_stats.dtype == torch.int64 and row_stats.numel() == B * H * W * 2 and col_s is not None and col_s.numel() >= Cout
     if CONV_TRACE is not None:  # tools/profile_frame.py: conv launches in issue order, to label an ncu launch list
         CONV_TRACE.append(dict(M=B * Ho * Wo, N=Cout, K=Cin * KH * KW, k=KH, s=stride, bn=block_n, act=act, gn=gn_groups,
                                f32=int(out.dtype == torch.float32)))
@@ -142,12 +145,14 @@ def dwconv7_ln(x, w49, bias, lnw, lnb, eps=1e-6, out=None):
     return out
 
 
-def dwconv7(x, w49, bias, out=None):
+def dwconv7(x, w49, bias, out=None, ln_stats=None):
     B, H, W, C = x.shape
     assert x.is_contiguous() and x.dtype == torch.bfloat16
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(_L().uc_dwconv7(_p(x), _p(w49), _p(bias), _p(out), B, H, W, C, _S()), "uc_dwconv7")
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.int64 and ln_stats.is_contiguous() and ln_stats.numel() == B * H * W * 2
+    _lib.check(_L().uc_dwconv7(_p(x), _p(w49), _p(bias), _p(out), B, H, W, C, _p(ln_stats), _S()), "uc_dwconv7")
     return out
 
 
