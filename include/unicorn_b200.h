@@ -207,6 +207,19 @@ UC_API int uc_dynamic_masks(const float* mask_feats, const float* up_masks, int 
                             const float* level_soi, const int* anchors_dev, const int* count_dev, int n_max, float* scratch,
                             float* out_masks, void* stream);
 
+/* VOS result assembly on the device (external/lib/test/tracker/unicorn_vos.py:129-155 mask resize to the original frame,
+ * :105-121 soft aggregation + argmax): for every object either `mask` (f32 [Hin,Win] soft mask at network resolution, resized
+ * with F.interpolate(scale_factor=1/r, bilinear, align_corners=False)[:H,:W]) or `init_mask` (uint8 [H,W] label map of the
+ * frame the object first appears in; object = label == id) or neither (no detection: zeros).  objs is a HOST array in the
+ * reference's list order (the float32 background product follows it).  soft_out (may be NULL) f32 [n,H,W]; seg_out uint8 [H,W]. */
+typedef struct UcVosObject {
+  const float* mask;
+  const uint8_t* init_mask;
+  int id;
+} UcVosObject;
+UC_API int uc_vos_aggregate(const UcVosObject* objs, int n, int Hin, int Win, int H, int W, float r, float* soft_out,
+                            uint8_t* seg_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

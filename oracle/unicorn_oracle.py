@@ -286,6 +286,17 @@ def head_forward(fpn, priors, sd, cfg, mode, decode=True, return_feats=False):
     return out
 
 
+def whole_forward(img, sd, cfg):
+    """Unicorn.forward(mode="whole") — unicorn.py:133-139: backbone + head on all-zero priors with the MOT prediction set.
+    Returns (head output, seq_dict); for a mask model the head output is UnicornHeadMask's tuple (head_forward_mask)."""
+    fpn, seq = forward_backbone(img, sd, cfg)
+    bs, _, H, W = img.shape
+    zeros = tuple(torch.zeros(bs, 1, H // s, W // s) for s in STRIDES)
+    if cfg["mask"]:
+        return head_forward_mask(fpn, zeros, sd, cfg, "mot"), seq
+    return head_forward(fpn, zeros, sd, cfg, "mot"), seq
+
+
 # ----------------------------------------------------------------------------------------------- post
 def box_iou_np(a, b):
     area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
@@ -480,3 +491,67 @@ def postprocess_inst(pred, locations, dyn, levels, mask_feats, up_masks, num_cla
     k = keep if max_masks is None else keep[:max_masks]
     masks = dynamic_masks(mask_feats, dyn[0][mask][k], locations[mask][k], levels[0][mask][k], up_masks, up_rate=8 // d_rate)
     return det, aligned_bilinear(masks, d_rate)
+
+
+# ----------------------------------------------------------------------------------------------- VOS driver (config 4)
+class VOSOracle:
+    """UnicornVOSTrack — external/lib/test/tracker/unicorn_vos.py: initialize :43-69, track :71-127 (groups of later objects
+    :79-98, soft aggregation :100-121), get_mask_results :129-155, get_det_results :157-201 — on pre-processed frames
+    (1,3,H,W) fp32 BGR 0..255, fp32 correlation (half_corr mimics the reference's fp16 casts)."""
+
+    def __init__(self, sd, cfg_name, conf=0.001, nms=0.65, d_rate=2, half_corr=False):
+        self.sd, self.cfg = sd, CONFIGS[cfg_name]
+        self.conf, self.nms, self.d_rate, self.half_corr = conf, nms, d_rate, half_corr
+
+    @torch.no_grad()
+    def initialize(self, ref_frame, boxes_xyxy, orig_size=None, r=1.0):
+        _, pre = forward_backbone(ref_frame, self.sd, self.cfg)
+        self.in_size = tuple(ref_frame.shape[-2:])
+        self.H, self.W = orig_size if orig_size is not None else self.in_size
+        self.r = r
+        self.dh, self.dw = pre["h"] * 2, pre["w"] * 2
+        self.groups = [(pre, list(boxes_xyxy.keys()))]
+        self.lbs = {o: label_map_s8(b, *self.in_size) for o, b in boxes_xyxy.items()}
+
+    def _group_results(self, fpn, cur, pre, ids):  # get_det_results + get_mask_results
+        f_pre, f_cur = deform_interaction(pre, cur, self.sd)
+        e_pre, e_cur = upsample_embed(f_pre, self.sd), upsample_embed(f_cur, self.sd)
+        out = {}
+        for o in ids:
+            pred = corr_propagate(e_pre.flatten(-2)[0], e_cur.flatten(-2)[0], self.lbs[o], half=self.half_corr)
+            coarse = pred.view(1, -1, self.dh, self.dw).float()
+            outs, locs, dyn, lvls, mf, um = head_forward_mask(fpn, prior_pyramid(coarse), self.sd, self.cfg, "sot")
+            det, masks = postprocess_inst(outs, locs, dyn, lvls, mf, um, 1, self.conf, self.nms, d_rate=self.d_rate, max_masks=1)
+            soft = np.zeros((self.H, self.W), dtype=np.float32)
+            if det is not None:
+                m = F.interpolate(masks, scale_factor=1 / self.r, mode="bilinear", align_corners=False)[:, 0, :self.H, :self.W]
+                soft[:m.shape[1], :m.shape[2]] = m[0].numpy()
+            out[o] = dict(det=None if det is None else det[0], soft=soft, coarse=coarse, head=outs, mask=None if det is None else masks[0, 0])
+        return out
+
+    @torch.no_grad()
+    def track(self, cur_frame, new_boxes_xyxy=None, init_mask=None):
+        """-> (segmentation uint8 (H,W), {obj_id: dict(det, soft, ...)}); new objects: boxes in resized-image coordinates and the
+        label map `init_mask` (H,W) of this frame."""
+        fpn, cur = forward_backbone(cur_frame, self.sd, self.cfg)
+        res = {}
+        for pre, ids in self.groups:
+            res.update(self._group_results(fpn, cur, pre, ids))
+        cur_ids = [o for _, ids in self.groups for o in ids]
+        if new_boxes_xyxy:
+            self.groups.append((cur, list(new_boxes_xyxy.keys())))
+            for o, b in new_boxes_xyxy.items():
+                self.lbs[o] = label_map_s8(b, *self.in_size)
+                res[o] = dict(det=None, soft=(np.asarray(init_mask) == int(o)))
+                cur_ids.append(o)
+        merge = np.zeros((self.H, self.W, max(int(o) for o in cur_ids) + 1))  # :106-117
+        tmp = []
+        for o in cur_ids:
+            merge[:, :, int(o)] = res[o]["soft"]
+            tmp.append(res[o]["soft"])
+        merge[:, :, 0] = np.prod(1 - np.stack(tmp, axis=-1), axis=-1, keepdims=False)
+        final = np.argmax(merge, axis=-1)
+        seg = np.zeros((self.H, self.W), dtype=np.uint8)
+        for o in cur_ids:
+            seg[final == int(o)] = int(o)
+        return seg, res

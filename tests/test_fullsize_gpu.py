@@ -122,3 +122,108 @@ def test_large_frame_vs_oracle_and_determinism():
     tol = dict(feat=4e-2, embed_cur=5e-2, fpn0=8e-2, fpn2=8e-2, coarse=6e-2, head_score=5e-2)
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
     assert not bad, f"out of tolerance: {bad} (all: {errs})"
+
+
+def _with_host_threads(fn):
+    from bench import host_threads
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(host_threads())  # the box shows 128 CPUs behind a 16-CPU cgroup quota
+    try:
+        with torch.no_grad():
+            return fn()
+    finally:
+        torch.set_num_threads(nthr)
+
+
+def test_mot_frame_1536x2048_vs_oracle():
+    """BASELINE configs[2]: one ConvNeXt-L 1536x2048 frame in `mode="whole"` (conv M = 49 152 pixels at stride 8, 64 512 anchors,
+    8 classes) + the QDTrack embedding branch, engine vs the CPU oracle (fp32); ~5.9 TFLOP of oracle work."""
+    import tracker_oracle as to
+    import unicorn_oracle as orc
+    from unicorn_b200 import ops
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.mot import UnicornMOTTracker
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.weights import make_state_dict
+    name, H, W = "unicorn_track_large", 1536, 2048
+    sd = make_state_dict(name, 0)
+    frames, _ = make_video(1, H, W, seed=2, n_obj=6)
+    eng = UnicornEngine(sd, name)
+    trk = UnicornMOTTracker(eng, (H, W), conf=0.01, nms=0.7)
+    trk.submit(frames[0:1])
+    torch.cuda.synchronize()
+    head = trk.last["head"].clone()
+    emb = trk.last["embed"].float().permute(0, 3, 1, 2).cpu()
+    n = int(trk.ws.count.item())
+    dets = trk.ws.dets[:n].cpu()
+    feats = trk.feats[:min(n, trk.max_dets)].cpu()
+    trk.collect()
+    assert head.shape == (1, 64512, 13) and torch.isfinite(head).all()
+    cfg = orc.CONFIGS[name]
+
+    def oracle():
+        o_head, seq = orc.whole_forward(frames[0:1], sd, cfg)
+        _, f_cur = orc.deform_interaction(seq, seq, sd)  # frame 1: pre_dict = cur_dict (mot_evaluator.py:1014-1015)
+        return o_head, orc.upsample_embed(f_cur, sd)
+    o_head, o_emb = _with_host_threads(oracle)
+    stride = torch.cat([torch.full((m,), float(s)) for m, s in ((192 * 256, 8), (96 * 128, 16), (48 * 64, 32))])
+    h = head.cpu()
+    errs = dict(xy=((h[0, :, :2] - o_head[0, :, :2]).abs().max(dim=1)[0] / stride).max().item(),
+                logwh=(torch.log(h[0, :, 2:4]) - torch.log(o_head[0, :, 2:4])).abs().max().item(),
+                score=(h[..., 4:] - o_head[..., 4:]).abs().max().item(),
+                embed=((emb - o_emb).abs().max() / o_emb.abs().max()).item())
+    print("1536x2048 MOT frame errors vs oracle:", {k: f"{v:.3e}" for k, v in errs.items()})
+    assert errs["xy"] < 0.2 and errs["logwh"] < 0.2 and errs["score"] < 5e-2 and errs["embed"] < 5e-2, errs
+    o_dets = orc.postprocess(o_head, 8, 0.01, 0.7)[0]
+    assert o_dets is not None and abs(n - o_dets.shape[0]) <= max(5, 0.05 * o_dets.shape[0]), (n, o_dets.shape)
+    # embedding sampling at the engine's own boxes against grid_sample on the engine's own map (a14, fp16 map)
+    k = min(n, 64)
+    ref_f = to.sample_embeddings(emb, dets[:k, :4], (H, W))
+    assert (feats[:k] - ref_f).abs().max().item() < 2e-3 * max(1.0, ref_f.abs().max().item())
+
+
+def test_vos_large_mask_3_objects_vs_oracle():
+    """BASELINE configs[3]: unicorn_track_large_mask at 800x1280 with three objects — propagated priors, per-object mask-head scores,
+    best-instance masks and the aggregated label map against the CPU oracle's VOS driver (fp32)."""
+    import unicorn_oracle as orc
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.vos import UnicornVOSTrack
+    from unicorn_b200.weights import make_state_dict
+    name, H, W = "unicorn_track_large_mask", 800, 1280
+    sd = make_state_dict(name, 0)
+    frames, boxes = make_video(2, H, W, seed=4, n_obj=3)
+    init = {str(i + 1): boxes[0, i] for i in range(3)}
+    vos = UnicornVOSTrack(UnicornEngine(sd, name), (H, W))
+    vos.debug = True
+    vos.initialize_tensor(frames[0:1], init)
+    out = vos.track_tensor(frames[1:2])
+    seg = out["segmentation"].cpu().numpy()
+
+    def oracle():
+        o = orc.VOSOracle(sd, name)
+        o.initialize(frames[0:1], init)
+        return o.track(frames[1:2])
+    o_seg, o_res = _with_host_threads(oracle)
+    report = {}
+    for oid in init:
+        det, mask = out["objects"][oid]
+        r = o_res[oid]
+        assert det is not None and r["det"] is not None
+        po = vos.last["per_obj"][oid]
+        report[oid] = dict(coarse=(vos.last["coarse"][oid].cpu() - r["coarse"][0]).abs().max().item(),
+                           score=(po["head"].cpu()[..., 4:] - r["head"][..., 4:]).abs().max().item(),
+                           top1_iou=float(orc.box_iou_np(det[None, :4].numpy(), r["det"][None, :4].numpy())[0, 0]))
+        mb, rb = mask.cpu() > 0.5, r["mask"] > 0.5
+        report[oid]["mask_iou"] = float((mb & rb).sum() / max(1, (mb | rb).sum()))
+        assert report[oid]["coarse"] < 6e-2 and report[oid]["score"] < 5e-2, report
+    agree = float((seg == o_seg).mean())
+    print("large-mask VOS, 3 objects:", report, "label agreement", agree)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        import json
+        json.dump(dict(per_object=report, label_agreement=agree), open(os.path.join(out_dir, "r2_vos_large_parity.json"), "w"), indent=1)
+    # where the engine picks the oracle's instance its mask must be the oracle's mask (bf16 features: IoU, not bit equality)
+    for oid, rr in report.items():
+        if rr["top1_iou"] > 0.9:
+            assert rr["mask_iou"] > 0.9, report

@@ -71,9 +71,10 @@ def test_vos_frame_vs_oracle_and_golden():
     frames, boxes = make_video(2, 320, 320, seed=0)
     eng = UnicornEngine(sd, name)
     vos = UnicornVOSTrack(eng, (320, 320), conf=float(g["conf"]), nms=float(g["nms"]))
+    vos.debug = True
     vos.initialize_tensor(frames[0:1], {"1": boxes[0, 0]})
     res = vos.track_tensor(frames[1:2])
-    det, mask = res["1"]
+    det, mask = res["objects"]["1"]
     assert det is not None
     # mask branch outputs vs the reference golden (bf16 path)
     mf = vos.last["mask_feats"].permute(0, 3, 1, 2).cpu()
@@ -88,6 +89,8 @@ def test_vos_frame_vs_oracle_and_golden():
     po = vos.last["per_obj"]["1"]
     head = po["head"].cpu()
     dyn = torch.cat([t[0, :, :, :169].reshape(-1, 169) for t in po["dyn"]], 0).cpu()[None]
+    # controller output (169 dynamic-conv parameters per anchor, unicorn_head_mask.py:333-334) vs the reference golden
+    assert rel(dyn[0, ::16], torch.from_numpy(g["dyn_sub"])) < 8e-2
     locs, lv = [], []
     for k, t in enumerate(po["dyn"]):
         a, b = t.shape[1:3]

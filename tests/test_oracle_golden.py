@@ -128,3 +128,46 @@ def test_mask_path_matches_reference_golden():
     assert (masks[0, 0, ::2, ::2] - torch.from_numpy(g["mask0_sub"].astype(np.float32))).abs().max().item() < 2e-3  # fixture is fp16
     area = (masks[:, 0] > 0.5).float().mean(dim=(1, 2)).numpy()
     assert np.allclose(area, g["mask_area"], atol=1e-4)
+
+
+def test_whole_mode_matches_reference_golden():
+    """`mode="whole"` (unicorn.py:133-139: zero priors, MOT prediction set of 8 classes) for the plain and the mask model
+    against tests/golden/whole_tiny_320.npz (outputs of the UNMODIFIED reference, tests/golden/make_golden_whole.py)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "whole_tiny_320.npz"))
+    frames, _ = make_video(2, 320, 320, seed=int(g["seed_video"]), n_obj=int(g["n_obj"]))
+    img = frames[int(g["frame"]):int(g["frame"]) + 1]
+    conf, nms = float(g["conf"]), float(g["nms"])
+    with torch.no_grad():
+        name = "unicorn_track_tiny"
+        head, seq = orc.whole_forward(img, make_state_dict(name, 0), orc.CONFIGS[name])
+        assert head.shape == (1, 2100, 13) and rel(head, g["head"]) < 1e-4 and rel(seq["feat"][0, ::4], g["feat_sub"]) < 1e-4
+        dets = orc.postprocess(head, 8, conf, nms)[0]
+        ref = torch.from_numpy(g["dets"])
+        assert dets.shape == ref.shape
+        assert torch.cdist(dets[:, :6], ref[:, :6], p=float("inf")).min(dim=0)[0].max().item() / ref[:, :6].abs().max().item() < 1e-4
+        name = "unicorn_track_tiny_mask"
+        (outs, locs, dyn, lvls, mf, um), _ = orc.whole_forward(img, make_state_dict(name, 0), orc.CONFIGS[name])
+        assert rel(outs, g["m_head"]) < 1e-4 and rel(dyn[0, ::16], g["m_dyn_sub"]) < 1e-4
+        assert rel(mf, g["m_mask_feats"]) < 1e-4 and rel(um[0, :, ::4, ::4], g["m_up_masks_sub"]) < 1e-4
+        md, mm = orc.postprocess_inst(outs, locs, dyn, lvls, mf, um, 8, conf, nms, d_rate=2, max_masks=int(g["keep"]))
+        assert md.shape == g["m_dets"].shape and rel(md[:, :6], g["m_dets"][:, :6]) < 1e-4
+        assert np.allclose((mm[:, 0] > 0.3).float().mean(dim=(1, 2)).numpy(), g["m_mask_area"], atol=1e-4)
+        assert (mm[0, 0, ::2, ::2] - torch.from_numpy(g["m_mask0_sub"].astype(np.float32))).abs().max().item() < 2e-3
+
+
+def test_vos_driver_matches_reference_class_golden():
+    """oracle.VOSOracle (two first-frame objects, a third appearing in frame 2, soft aggregation, resize to the original frame)
+    against the label maps produced by the UNMODIFIED reference class UnicornVOSTrack (tests/golden/make_golden_vos.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_vos_common import make_sequence, prep_frame, box_xyxy
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vos_tiny.npz"))
+    name, size = str(g["config"]), tuple(int(v) for v in g["size"])
+    H0, W0, new_at = int(g["H0"]), int(g["W0"]), int(g["new_at"])
+    rgb, xywh, lab = make_sequence()
+    r = min(size[0] / H0, size[1] / W0)
+    o = orc.VOSOracle(make_state_dict(name, 0), name, half_corr=True)
+    o.initialize(prep_frame(rgb[0], size), {"1": box_xyxy(xywh[0, 0], r), "2": box_xyxy(xywh[0, 1], r)}, orig_size=(H0, W0), r=r)
+    for t in range(1, int(g["n_frames"])):
+        new = {"3": box_xyxy(xywh[t, 2], r)} if t == new_at else None
+        seg, _ = o.track(prep_frame(rgb[t], size), new, lab if t == new_at else None)
+        assert (seg == g["segs"][t - 1]).mean() > 0.999

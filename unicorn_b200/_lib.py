@@ -28,6 +28,10 @@ class UcConv2d(ctypes.Structure):
     ]
 
 
+class UcVosObject(ctypes.Structure):
+    _fields_ = [("mask", ctypes.c_void_p), ("init_mask", ctypes.c_void_p), ("id", ctypes.c_int)]
+
+
 _lib = None
 
 
@@ -45,8 +49,6 @@ def lib():
                 "(unicorn_b200 has no CPU/PyTorch fallback path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.uc_last_error.restype = ctypes.c_char_p
-        for name in dir(_lib):
-            pass
     return _lib
 
 

@@ -8,6 +8,7 @@
 #include "uc_common.h"
 #include "../../include/unicorn_b200.h"
 #include <algorithm>
+#include <cmath>
 
 namespace uc {
 
@@ -158,6 +159,63 @@ __global__ void __launch_bounds__(256) mask_final_up_kernel(const float* __restr
                                              fy * ((1.f - fx) * s[y1 * ws + x0] + fx * s[y1 * ws + x1]);
 }
 
+
+// ------------------------------------------------------------------------------------------------ VOS soft aggregation
+// external/lib/test/tracker/unicorn_vos.py:129-155 (resize of every object's best mask to the original frame:
+// F.interpolate(scale_factor=1/r, bilinear, align_corners=False)[:H, :W] into a zero map) and :105-121 (soft aggregation:
+// background = prod_i (1 - m_i) in float32 in list order, argmax over [background, m_id...] with the lower channel winning
+// ties, label = object id).  One thread per original-frame pixel; the resized soft masks are optional outputs.
+constexpr int kVosMaxObj = 16;
+struct VosObjs {
+  const float* mask[kVosMaxObj];       // network-resolution soft mask [Hin, Win] or nullptr
+  const uint8_t* init_mask[kVosMaxObj];  // original-frame label map [H, W]: object = (label == id), or nullptr
+  int id[kVosMaxObj];
+  int by_id[kVosMaxObj];  // object indices in ascending id order (argmax tie-breaking)
+  int n;
+};
+
+__global__ void __launch_bounds__(256) vos_aggregate_kernel(VosObjs o, int Hin, int Win, int H, int W, int hm, int wm, float scale,
+                                                             float* __restrict__ soft, uint8_t* __restrict__ seg) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long total = static_cast<long>(H) * W;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+    float m[kVosMaxObj];
+    const bool inside = y < hm && x < wm;
+    int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+    float ly = 0.f, lx = 0.f;
+    if (inside) {  // PyTorch's source index rule (see bilinear_kernel in misc_kernels.cu)
+      const float fy = fmaxf((y + 0.5f) * scale - 0.5f, 0.f), fx = fmaxf((x + 0.5f) * scale - 0.5f, 0.f);
+      y0 = min(static_cast<int>(fy), Hin - 1); x0 = min(static_cast<int>(fx), Win - 1);
+      y1 = min(y0 + 1, Hin - 1); x1 = min(x0 + 1, Win - 1);
+      ly = fy - y0; lx = fx - x0;
+    }
+    float bg = 1.f;
+#pragma unroll 1
+    for (int k = 0; k < o.n; ++k) {
+      float v = 0.f;
+      if (o.init_mask[k]) {
+        v = o.init_mask[k][i] == static_cast<uint8_t>(o.id[k]) ? 1.f : 0.f;
+      } else if (o.mask[k] && inside) {
+        const float* s = o.mask[k];
+        v = (1.f - ly) * ((1.f - lx) * s[y0 * Win + x0] + lx * s[y0 * Win + x1]) + ly * ((1.f - lx) * s[y1 * Win + x0] + lx * s[y1 * Win + x1]);
+      }
+      m[k] = v;
+      if (soft) soft[static_cast<long>(k) * total + i] = v;
+      bg = bg * (1.f - v);
+    }
+    float best = bg;
+    int label = 0;
+#pragma unroll 1
+    for (int t = 0; t < o.n; ++t) {
+      const int k = o.by_id[t];
+      if (m[k] > best) { best = m[k]; label = o.id[k]; }
+    }
+    seg[i] = static_cast<uint8_t>(label);
+  }
+}
+
 }  // namespace uc
 
 using namespace uc;
@@ -198,4 +256,25 @@ extern "C" int uc_dynamic_masks(const float* mask_feats, const float* up_masks, 
     launch_pdl(mask_final_up_kernel, dim3((H2 * W2 + 255) / 256, n_max), 256, 0, stream, mid, H1, W1, d_rate, count_dev, n_max, out_masks);
   }
   return check_launch("uc_dynamic_masks");
+}
+
+extern "C" int uc_vos_aggregate(const UcVosObject* objs, int n, int Hin, int Win, int H, int W, float r, float* soft_out, uint8_t* seg_out,
+                                void* stream_v) {
+  if (!objs || !seg_out || n < 1 || n > kVosMaxObj) return set_error(UC_EINVAL, "uc_vos_aggregate: 1..%d objects", kVosMaxObj);
+  if (Hin < 1 || Win < 1 || H < 1 || W < 1 || !(r > 0.f)) return set_error(UC_EINVAL, "uc_vos_aggregate: bad sizes");
+  VosObjs o;
+  memset(&o, 0, sizeof(o));
+  o.n = n;
+  for (int k = 0; k < n; ++k) {
+    if (objs[k].id < 1 || objs[k].id > 255) return set_error(UC_EINVAL, "uc_vos_aggregate: object ids must be 1..255");
+    o.mask[k] = objs[k].mask; o.init_mask[k] = objs[k].init_mask; o.id[k] = objs[k].id; o.by_id[k] = k;
+  }
+  std::stable_sort(o.by_id, o.by_id + n, [&](int a, int b) { return o.id[a] < o.id[b]; });
+  // F.interpolate(scale_factor = 1/r): output size floor(in * (1/r)) in double precision, source scale 1 / (1/r) as a float
+  const double sf = 1.0 / static_cast<double>(r);
+  const int hm = std::min(H, static_cast<int>(std::floor(Hin * sf))), wm = std::min(W, static_cast<int>(std::floor(Win * sf)));
+  const long total = static_cast<long>(H) * W;
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16)));
+  launch_pdl(vos_aggregate_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), o, Hin, Win, H, W, hm, wm, static_cast<float>(1.0 / sf), soft_out, seg_out);
+  return check_launch("uc_vos_aggregate");
 }

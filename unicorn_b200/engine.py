@@ -395,14 +395,24 @@ class UnicornEngine:
             self._pos_cache[key] = (toks.to(BF16).contiguous(), pos)
         return self._pos_cache[key]
 
-    def project_tokens(self, feat, lvl, src, q):
-        """bottleneck conv1x1+bias -> GN32 (unicorn.py:36-38,265); writes rows of `src` and `q = src + pos + level_embed`."""
+    def project_tokens(self, feat, lvl, src_rows, q_rows):
+        """bottleneck conv1x1+bias -> GN32 (unicorn.py:36-38,265); writes `src_rows` [h*w, 256] and
+        `q_rows = src + pos + level_embed[lvl]`."""
         h, w = feat.shape[1:3]
         pos_lvl = self.pos_tokens(h, w)[0]
-        n = h * w
-        dst = src[lvl * n:(lvl + 1) * n].view(1, h, w, 256)
-        self.conv_gn(feat, self.P["bottleneck"], dst, act=ACT_NONE, add2=pos_lvl[lvl].view(1, h, w, 256),
-                     out2=q[lvl * n:(lvl + 1) * n].view(1, h, w, 256))
+        self.conv_gn(feat, self.P["bottleneck"], src_rows.view(1, h, w, 256), act=ACT_NONE, add2=pos_lvl[lvl].view(1, h, w, 256),
+                     out2=q_rows.view(1, h, w, 256))
+
+    def project_ref(self, feat):
+        """Projection of a fixed reference frame (level 0 of the encoder input), computed once and OWNED BY THE CALLER: several
+        trackers may share one engine, each keeps its own reference (the reference repo keeps `out_dict_pre` per tracker,
+        unicorn_sot.py:47).  Pass the result to interaction(ref_proj=...)."""
+        h, w = feat.shape[1:3]
+        src = torch.empty(h * w, 256, dtype=BF16, device=self.dev)
+        q = torch.empty(h * w, 256, dtype=BF16, device=self.dev)
+        self.begin_frame()
+        self.project_tokens(feat, 0, src, q)
+        return src, q
 
     def encoder(self, src, q, h, w):
         """One deformable encoder layer over the two frames as two levels (deformable_transformer.py:122-131,
@@ -419,15 +429,18 @@ class UnicornEngine:
         ops.layernorm(y, *P["norm2"], 1e-5, out=y)
         return y
 
-    def interaction(self, feat0, feat1, cache_ref=False):
+    def interaction(self, feat0, feat1, ref_proj=None):
         """Unicorn.forward_deform_interact (unicorn.py:260-276): -> (new_feat0, new_feat1) NHWC bf16 [1,h,w,256].
-        cache_ref=True reuses the rows of frame 0 already projected by a previous call (fixed SOT reference)."""
+        ref_proj = project_ref(feat0) of a fixed reference frame: its rows are copied in instead of being recomputed."""
         h, w = feat1.shape[1:3]
         n = h * w
         src, q = self.buf("enc.src", (2 * n, 256)), self.buf("enc.q", (2 * n, 256))
-        if not cache_ref:
-            self.project_tokens(feat0, 0, src, q)
-        self.project_tokens(feat1, 1, src, q)
+        if ref_proj is None:
+            self.project_tokens(feat0, 0, src[:n], q[:n])
+        else:
+            src[:n].copy_(ref_proj[0])
+            q[:n].copy_(ref_proj[1])
+        self.project_tokens(feat1, 1, src[n:], q[n:])
         y = self.encoder(src, q, h, w)
         return y[:n].view(1, h, w, 256), y[n:].view(1, h, w, 256)
 

@@ -69,7 +69,7 @@ class UnicornSOTTrack:
         e = self.eng
         e.begin_frame()
         def correlate(seq):  # runs on a second stream while the neck runs on the main one
-            f_pre, f_cur = e.interaction(self.ref_feat, seq["feat"], cache_ref=True)
+            f_pre, f_cur = e.interaction(self.ref_feat, seq["feat"], ref_proj=self.ref_proj)
             e_pre, e_cur = e.upsample(f_pre, "embp"), e.upsample(f_cur, "embc")
             return f_pre, f_cur, e_pre, e_cur, e.propagate(e_pre, e_cur, self.lbs_pre)
 
@@ -93,11 +93,8 @@ class UnicornSOTTrack:
         inp = self._stage_input(ref_frame)
         e.begin_frame()
         _, seq = e.backbone(inp, tag="ref")
-        self.ref_feat = seq["feat"]
-        h, w = seq["h"], seq["w"]
-        n = h * w
-        src, q = e.buf("enc.src", (2 * n, 256)), e.buf("enc.q", (2 * n, 256))
-        e.project_tokens(self.ref_feat, 0, src, q)
+        self.ref_feat = seq["feat"].clone()
+        self.ref_proj = e.project_ref(self.ref_feat)  # this tracker's own copy (several trackers may share the engine)
         lab = get_label_map(init_box_xyxy, H, W, e.dev)
         self.lbs_pre = ops.bilinear(lab, H // 8, W // 8, 8.0, 8.0).reshape(1, -1).contiguous()
         self.graph = None
