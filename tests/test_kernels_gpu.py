@@ -47,7 +47,9 @@ def test_dwconv_ln(C, H, W, B):
     close(out, ref, 6e-3, "dwconv_ln")
 
 
-@pytest.mark.parametrize("C,H,W", [(96, 20, 28), (192, 17, 23), (256, 10, 16), (1536, 5, 9), (384, 33, 40)])
+@pytest.mark.parametrize("C,H,W", [(96, 20, 28), (192, 17, 23), (256, 10, 16), (1536, 5, 9), (384, 33, 40),
+                                   # ConvNeXt-L layer shapes at 800x1280 (TMA kernel: 16x4-pixel x 64-channel items, edge tiles, 24 chunks)
+                                   (768, 50, 80), (192, 200, 320), (1536, 25, 40), (256, 100, 160), (104, 9, 3)])
 def test_dwconv_tiled(C, H, W):
     from unicorn_b200 import ops
     g = G(21)

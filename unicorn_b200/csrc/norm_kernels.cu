@@ -682,8 +682,10 @@ extern "C" int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* 
   return check_launch("uc_dwconv7_ln");
 }
 
-extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
-                          void* ln_stats, void* stream_v) {
+// cp.async-staged depthwise kernel: the fallback of uc_dwconv7 (csrc/dwconv_tma.cu) for maps the TMA path cannot describe
+// (C % 8 != 0 / unaligned pointers) and the A/B reference for it (UC_DW_TILED=1).  Not part of the public C ABI.
+extern "C" int uc_dwconv7_tiled(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
+                                void* ln_stats, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!x_bf16 || !w49 || !bias || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7: null pointer");
   if (C % 32) return set_error(UC_EINVAL, "uc_dwconv7: C must be a multiple of 32");
