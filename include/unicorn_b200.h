@@ -142,6 +142,11 @@ UC_API int uc_bilinear_f32(const float* src, float* dst, int P, int Hs, int Ws, 
 UC_API int uc_letterbox_u8(const uint8_t* src_hwc, int Hs, int Ws, uint8_t* dst_hwc, int Hd, int Wd, int rh, int rw,
                            int swap_rb, int pad, void* stream);
 UC_API int uc_add(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long M, int C, int dtype, void* stream);
+/* Conditional strided row copy decided on the device: rows are copied when (*flag_dev != 0) != invert.  The MOT drivers use it for
+ * "pre_dict = cur_dict only when this frame produced detections" (unicorn/evaluators/mot_evaluator.py:1005,1014-1020) so that the
+ * frame needs no host decision (CUDA-graph replay).  16-byte aligned rows / strides. */
+UC_API int uc_copy_rows_if(const int* flag_dev, int invert, const void* src, long src_ld_bytes, void* dst, long dst_ld_bytes, long rows,
+                           int row_bytes, void* stream);
 UC_API int uc_nchw_f32_to_nhwc(const float* src, void* dst, int ldd, int B, int C, long HW, int dtype, void* stream);
 UC_API int uc_nhwc_to_nchw_f32(const void* src, int lds, float* dst, int B, int C, long HW, int dtype, void* stream);
 

@@ -79,11 +79,17 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 int num_sms() {
-  static int n = 0;
+  static PerDeviceInt cache;
+  int& n = cache.get();
   if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, cur_device()) != cudaSuccess) {
       cudaGetLastError();
       n = 148;
     }

@@ -487,7 +487,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_gemm_kernel(const __grid_co
 template <int BLOCK_N, int STAGES, int CLUSTER>
 static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256 + kGnSmemBytes;
-  static int per_sm = 0;
+  static PerDeviceInt per_sm_dev;
+  int& per_sm = per_sm_dev.get();
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>;
   if (!per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
 template <int NOBJ>
 static int launch_corr(const CorrParams& p, int grid, cudaStream_t stream) {
   constexpr int smem = (1 + kCorrStages) * kCorrTileBytes + 2 * NOBJ * kCorrTile * 4 + 256 + 1024;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_dev;
+  bool& attr_set = attr_dev.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(corr_kernel<NOBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "corr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -211,7 +211,8 @@ extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bia
   const long items = static_cast<long>(p.tiles_w) * p.tiles_h * B * ((C + kDwCCH - 1) / kDwCCH);
   if (items > 0x7fffffffL) return set_error(UC_EINVAL, "uc_dwconv7: too many tiles");
   p.n_items = static_cast<int>(items);
-  static bool attr = false;
+  static PerDeviceFlag attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "uc_dwconv7: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

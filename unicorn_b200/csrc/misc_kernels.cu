@@ -188,6 +188,23 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint16_t* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ conditional row copy
+// dst rows <- src rows when (*flag != 0) != invert, else nothing: device-side "pre_dict = cur_dict only if this frame had
+// detections" (unicorn/evaluators/mot_evaluator.py:1005,1014-1020) without a host round trip, so the MOT frame stays one CUDA graph.
+__global__ void __launch_bounds__(256) copy_rows_if_kernel(const int* __restrict__ flag, int invert, const uint8_t* __restrict__ src, long src_ld,
+                                                            uint8_t* __restrict__ dst, long dst_ld, long rows, int row_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if ((*flag != 0) == (invert != 0)) return;
+  const long total = rows * row_chunks;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / row_chunks;
+    const int c = static_cast<int>(i % row_chunks);
+    *reinterpret_cast<uint4*>(dst + r * dst_ld + c * 16) = *reinterpret_cast<const uint4*>(src + r * src_ld + c * 16);
+  }
+}
+
 static inline int grid_for(long total, int per_block = 256) {
   return static_cast<int>(std::max<long>(1, std::min<long>((total + per_block - 1) / per_block, static_cast<long>(num_sms()) * 16)));
 }
@@ -253,4 +270,14 @@ extern "C" int uc_nhwc_to_nchw_f32(const void* src, int lds, float* dst, int B, 
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(B));
   launch_pdl(nhwc_to_nchw_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream_v), static_cast<const uint16_t*>(src), lds, dst, B, C, HW, dtype);
   return check_launch("uc_nhwc_to_nchw_f32");
+}
+
+extern "C" int uc_copy_rows_if(const int* flag_dev, int invert, const void* src, long src_ld_bytes, void* dst, long dst_ld_bytes, long rows,
+                               int row_bytes, void* stream_v) {
+  if (!flag_dev || !src || !dst || rows < 1 || row_bytes < 16 || row_bytes % 16 || src_ld_bytes % 16 || dst_ld_bytes % 16 ||
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15))
+    return set_error(UC_EINVAL, "uc_copy_rows_if: 16-byte aligned rows only");
+  launch_pdl(copy_rows_if_kernel, grid_for(rows * (row_bytes / 16)), 256, 0, static_cast<cudaStream_t>(stream_v), flag_dev, invert,
+             static_cast<const uint8_t*>(src), src_ld_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes, rows, row_bytes / 16);
+  return check_launch("uc_copy_rows_if");
 }

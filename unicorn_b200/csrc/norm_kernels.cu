@@ -414,7 +414,8 @@ static bool launch_dwln(const void* x, const float* w49, const float* bias, cons
   const int tiles_w = (W + TW - 1) / TW, tiles = tiles_w * ((H + TH - 1) / TH);
   if (smem > 227 * 1024) return false;
   if (!force && static_cast<long>(tiles) * B < 100) return false;  // too few CTAs for 148 SMs: try a smaller tile
-  static int smem_set = 0;
+  static PerDeviceInt smem_dev;
+  int& smem_set = smem_dev.get();
   auto kern = dwln_kernel<TW, TH, PX, NT>;
   if (smem > smem_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
   launch_pdl(kern, dim3(tiles, B), NT, smem, stream, static_cast<const uint16_t*>(x), w49, bias, lnw, lnb, static_cast<uint16_t*>(y), H, W, C,
@@ -692,7 +693,8 @@ extern "C" int uc_dwconv7_tiled(const void* x_bf16, const float* w49, const floa
   const int tiles_w = (W + 15) / 16;
   if (C % 64 == 0) {
     constexpr int smem = (8 + 6) * 22 * 128 + 49 * 64 * 4;
-    static bool attr = false;
+    static PerDeviceFlag attr_dev;
+    bool& attr = attr_dev.get();
     if (!attr) { cudaFuncSetAttribute(dwconv7_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     dim3 grid(tiles_w * ((H + 7) / 8), C / 64, B);
     launch_pdl(dwconv7_tiled_kernel<64>, grid, 512, smem, stream, static_cast<const uint16_t*>(x_bf16), w49, bias, static_cast<uint16_t*>(y_bf16), H, W, C, tiles_w, static_cast<long long*>(ln_stats));

@@ -306,7 +306,8 @@ extern "C" int uc_postprocess(const float* pred, int A, int ncls, float conf_thr
   launch_pdl(sort_desc_kernel, 1, 1024, 0, stream, keys, count, static_cast<int>(a2));
   launch_pdl(det_gather_kernel, std::min(num_sms() * 4, (A + 255) / 256), 256, 0, stream, det, keys, count, sorted, det_anchor, sorted_anchor);
   constexpr int smem = kNmsKeepSmem * (16 + 4);
-  static bool attr = false;
+  static PerDeviceFlag attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;

@@ -17,6 +17,18 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
                 const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 int check_launch(const char* what);
 int num_sms();
+// One-time per-DEVICE state (cudaFuncSetAttribute, occupancy queries are per device): a process that drives several GPUs must not
+// reuse what it cached for the first one.
+constexpr int kMaxDevices = 64;
+int cur_device();  // cudaGetDevice, clamped to [0, kMaxDevices)
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool& get() { return done[cur_device()]; }
+};
+struct PerDeviceInt {
+  int v[kMaxDevices] = {};
+  int& get() { return v[cur_device()]; }
+};
 bool pdl_enabled();  // UC_PDL=0 in the environment turns programmatic dependent launch off (plain stream order)
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may become resident while its predecessor in

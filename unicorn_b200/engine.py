@@ -239,6 +239,10 @@ class UnicornEngine:
 
     def begin_frame(self):
         """Zero the GroupNorm statistics arena (one memset per frame; slots are handed out in call order)."""
+        # every launch goes to the CURRENT device's current stream (ops._S): an engine living on another GPU must be driven under
+        # torch.cuda.device(engine.dev) — one process per GPU is the intended deployment (DESIGN.md 6)
+        assert self.dev.index is None or torch.cuda.current_device() == self.dev.index, \
+            f"UnicornEngine on {self.dev} driven while cuda:{torch.cuda.current_device()} is current: wrap the calls in torch.cuda.device(...)"
         if self._stats_arena is None:
             self._stats_arena = torch.zeros(512, 32, 2, dtype=torch.int64, device=self.dev)
         else:

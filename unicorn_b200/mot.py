@@ -38,7 +38,11 @@ class UnicornMOTTracker:
         self.feats = torch.zeros(max_dets, 128, dtype=torch.float32, device=dev)
         self.frame_id = 0       # frames submitted
         self.collected = 0      # frames associated
-        self._prev_feat = None
+        # pre_dict of the reference loop (mot_evaluator.py:1014-1020): the s16 feature of the last frame THAT HAD DETECTIONS, kept in
+        # its own buffer and updated by a device-side conditional copy (no host decision inside the frame)
+        self._prev_feat = torch.zeros(1, H // 16, W // 16, engine.dims[2], dtype=torch.bfloat16, device=dev)
+        self._has_prev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._warned = False
         # two pinned result slots: at most one frame is in flight behind the one being associated
         self._slots = [dict(cnt=torch.zeros(1, dtype=torch.int32).pin_memory(), dets=torch.zeros(max_dets, 7).pin_memory(),
                             feats=torch.zeros(max_dets, 128).pin_memory(), ev=torch.cuda.Event(), scale=1.0, frame_id=0)
@@ -57,11 +61,14 @@ class UnicornMOTTracker:
         dets, cnt = ops.postprocess_device(out[0], e.ncls, self.conf, self.nms, self.ws)
         emb = None
         if self.assoc == "qd":
-            prev = self._prev_feat if self._prev_feat is not None else seq["feat"]  # frame 1: pre_dict = cur_dict (:1014-1015)
-            _, f_cur = e.interaction(prev, seq["feat"])
+            # first frame with detections: pre_dict = cur_dict (:1014-1015); afterwards pre_dict advances only on frames that
+            # produced detections (the reference skips its whole tracking block when outputs[0] is None, :1005)
+            ops.copy_rows_if(self._has_prev, seq["feat"], self._prev_feat, invert=True)
+            _, f_cur = e.interaction(self._prev_feat, seq["feat"])
             emb = e.upsample(f_cur, "mot.emb")
             ops.sample_embed(emb, dets, self.max_dets, 8.0, count=cnt, out=self.feats)
-        self._prev_feat = seq["feat"]
+            ops.copy_rows_if(cnt, seq["feat"], self._prev_feat)
+            self._has_prev.bitwise_or_((cnt > 0).to(torch.int32))
         self.last = dict(embed=emb, head=out)
 
     def submit(self, frame, scale=1.0):
@@ -75,14 +82,14 @@ class UnicornMOTTracker:
             if g is None:  # frames 1-2 ran eagerly (plan-time autotuning, first-frame special case); 3 and 4 are captured
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                keep = (self._prev_feat, self.last)
+                keep = self.last
                 with torch.cuda.graph(g):
                     self._device_frame(parity)
-                self._graphs[parity] = (g, self._prev_feat, self.last)
-                self._prev_feat, self.last = keep
+                self._graphs[parity] = (g, self.last)
+                self.last = keep
                 g = self._graphs[parity]
             g[0].replay()
-            self._prev_feat, self.last = g[1], g[2]
+            self.last = g[1]
         else:
             self._device_frame(parity)
         s = self._slots[parity]
@@ -102,7 +109,13 @@ class UnicornMOTTracker:
         self.collected += 1
         s = self._slots[self.collected & 1]
         s["ev"].synchronize()
-        n = min(int(s["cnt"][0]), self.max_dets)
+        total = int(s["cnt"][0])
+        if total > self.max_dets and not self._warned:
+            import warnings
+            warnings.warn(f"UnicornMOTTracker: {total} detections after NMS, only the {self.max_dets} best are associated "
+                          "(raise max_dets; the reference has no cap)")
+            self._warned = True
+        n = min(total, self.max_dets)
         d = s["dets"][:n].clone()
         if self.assoc == "byte":
             H, W = self.input_size
@@ -114,8 +127,9 @@ class UnicornMOTTracker:
         boxes = torch.cat([d[keep, :4] / s["scale"], scores[keep, None]], 1)
         labels = torch.ones(boxes.size(0))  # :1013 (all labels = 1)
         self.last.update(dets=d, feats=f)
-        if boxes.size(0) == 0:
+        if n == 0:  # outputs[0] is None: the reference skips tracking for this frame altogether (:1005)
             return torch.zeros(0, 5), torch.zeros(0, dtype=torch.long)
+        # detections exist but none may pass the score filter: match() still runs (tracklets age, backdrops are replaced)
         ob, _, oid = self.tracker.match(boxes, labels, f[keep], s["frame_id"])
         valid = oid > -1  # :1047-1053
         ob, oid = ob[valid], oid[valid]

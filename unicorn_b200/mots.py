@@ -26,7 +26,8 @@ class UnicornMOTSTracker:
         self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=engine.dev)
         self.feats = torch.zeros(max_dets, 128, dtype=torch.float32, device=engine.dev)
         self.frame_id = 0
-        self._prev_feat = None
+        self._prev_feat = torch.zeros(1, H // 16, W // 16, engine.dims[2], dtype=torch.bfloat16, device=engine.dev)
+        self._has_prev = torch.zeros(1, dtype=torch.int32, device=engine.dev)
         self.last = {}
 
     def step_tensor(self, frame, img_h, img_w):
@@ -43,11 +44,12 @@ class UnicornMOTSTracker:
         mf, um = e.mask_branch(fpn)
         hw = [(t.shape[1], t.shape[2]) for t in e.dyn_levels]
         masks = ops.dynamic_masks(mf, um, e.dyn_levels, hw, self.ws, self.max_dets, up_rate=8 // self.d_rate, d_rate=self.d_rate)
-        prev = self._prev_feat if self._prev_feat is not None else seq["feat"]  # frame 1: pre_dict = cur_dict (:812-813)
-        _, f_cur = e.interaction(prev, seq["feat"])
+        ops.copy_rows_if(self._has_prev, seq["feat"], self._prev_feat, invert=True)  # first frame with detections: pre_dict = cur_dict (:812-813)
+        _, f_cur = e.interaction(self._prev_feat, seq["feat"])
         emb = e.upsample(f_cur, "mots.emb")
-        self._prev_feat = seq["feat"]
         ops.sample_embed(emb, dets, self.max_dets, 8.0, count=cnt, out=self.feats)
+        ops.copy_rows_if(cnt, seq["feat"], self._prev_feat)  # pre_dict advances only on frames with detections (:803,818)
+        self._has_prev.bitwise_or_((cnt > 0).to(torch.int32))
         n = min(int(cnt.item()), self.max_dets)
         d, f = dets[:n].cpu(), self.feats[:n].cpu()
         scale = min(H / float(img_h), W / float(img_w))
@@ -58,7 +60,7 @@ class UnicornMOTSTracker:
         boxes = torch.cat([d[keep, :4] / scale, scores[keep, None]], 1)
         m, f = m[keep.to(m.device)], f[keep]
         self.last = dict(dets=d, masks=masks[:n], head=out, mask_feats=mf, up_masks=um, dyn=[t for t in e.dyn_levels])
-        if boxes.size(0) == 0:
+        if n == 0:  # outputs[0] is None: no tracking for this frame (mot_evaluator.py:803)
             return self.frame_id, [], 2, img_h, img_w, []
         ob, _, oid, idx = self.tracker.match(boxes, torch.ones(boxes.size(0)), f, self.frame_id, return_index=True)
         m = m[idx.to(m.device)]

@@ -212,6 +212,17 @@ def add(a2d, b2d, out=None):
     return out
 
 
+def copy_rows_if(flag, src, dst, invert=False):
+    """dst <- src (NHWC views of equal shape, channel-contiguous) when (flag[0] != 0) != invert — decided on the device."""
+    assert src.shape == dst.shape and src.dtype == dst.dtype and flag.dtype == torch.int32
+    C = src.shape[-1]
+    rows = src.numel() // C
+    es = src.element_size()
+    _lib.check(_L().uc_copy_rows_if(_p(flag), int(bool(invert)), _p(src), _l(_nhwc_ld(src) * es), _p(dst), _l(_nhwc_ld(dst) * es), _l(rows), C * es, _S()),
+               "uc_copy_rows_if")
+    return dst
+
+
 def letterbox_u8(src, input_size, swap_rb=True, pad=114, out=None):
     """src: uint8 [h,w,3] device tensor (RGB when swap_rb) -> (uint8 [1,H,W,3] letterboxed frame, r) — the preprocessing of
     external/lib/test/tracker/unicorn_sot.py:114-123 (swap_rb=True) / data_augment.py:194-214 (swap_rb=False)."""

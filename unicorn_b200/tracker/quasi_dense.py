@@ -56,9 +56,13 @@ class QuasiDenseEmbedTracker:
 
     # ---------------------------------------------------------------------------------------------- match
     def match(self, bboxes, labels, track_feats, frame_id, asso_tau=-1, return_index=False):
+        # the caller's label tensor (dtype, device) is what comes back, like the reference which only indexes it; the float copy
+        # below feeds the class gate of the score kernel and the memo
+        labels_in, out_dev = labels, bboxes.device
         bboxes, labels, track_feats = bboxes.detach().cpu().float(), labels.detach().cpu().float(), track_feats.detach().cpu().float()
         order = bboxes[:, -1].sort(descending=True)[1]
         bboxes, labels, embeds = bboxes[order], labels[order], track_feats[order]
+        labels_in = labels_in[order.to(labels_in.device)]
         n = bboxes.size(0)
         # duplicate removal: a box is dropped if ANY higher-scored box (kept or not) overlaps it above its threshold
         valids = torch.ones(n, dtype=torch.bool)
@@ -68,6 +72,7 @@ class QuasiDenseEmbedTracker:
             over = torch.tril(iou > thr[:, None], diagonal=-1)  # row i vs columns < i
             valids = ~over.any(dim=1)
         bboxes, labels, embeds = bboxes[valids], labels[valids], embeds[valids]
+        labels_in = labels_in[valids.to(labels_in.device)]
         n = bboxes.size(0)
         ids = torch.full((n,), -1, dtype=torch.long)
         if n > 0 and not self.empty:
@@ -93,8 +98,8 @@ class QuasiDenseEmbedTracker:
         self.num_tracklets += n_new
         self._update_memo(ids, bboxes, embeds, labels, frame_id)
         if return_index:
-            return bboxes, labels, ids, valids
-        return bboxes, labels, ids
+            return bboxes.to(out_dev), labels_in, ids.to(out_dev), valids.to(out_dev)
+        return bboxes.to(out_dev), labels_in, ids.to(out_dev)
 
     # ---------------------------------------------------------------------------------------------- memo
     def _update_memo(self, ids, bboxes, embeds, labels, frame_id):
