@@ -6,9 +6,9 @@ are compared frame by frame.
     (IoU < 0.5).  With seeded random weights the best scores are nearly tied (0.0120 / 0.0115 / 0.0111 ...), so a flip is only a
     defect when the decision is well conditioned: oracle margin s1 - s2 larger than twice the largest score error the engine
     makes on that frame.  Bound: NO flip among well-conditioned frames; the overall rate is reported.
-  * MOT (mot_evaluator.py:1005-1057 + QuasiDenseEmbedTracker): ids of the engine's tracks against the oracle tracker's ids on
-    the oracle's detections.  Tracks are paired by box IoU > 0.7 in each frame; the first pairing of an engine id fixes its
-    oracle id, every later frame in which the pairing differs is an id flip.  Bound: <= 10 % of paired track-frames.
+  * MOT (mot_evaluator.py:1005-1057 + QuasiDenseEmbedTracker): (a) ids from engine embeddings vs oracle embeddings on identical
+    boxes must match bit for bit; (b) the raw end-to-end id-flip count (each side on its own detections; tracks paired by box
+    IoU > 0.7, first pairing fixes the id map, later disagreements are flips) is reported.
 
 The measured rates are printed and written to gpurun_out/r2_fliprate.json (copied to profiles/ by hand)."""
 import json
@@ -71,21 +71,80 @@ def test_sot_top1_flip_rate():
     assert hard_flips == 0, REPORT["sot"]
 
 
-def test_mot_id_flip_rate():
-    import tracker_oracle as to
+def _mot_models():
     import unicorn_oracle as orc
     from unicorn_b200.engine import UnicornEngine
-    from unicorn_b200.mot import UnicornMOTTracker
-    from unicorn_b200.synthetic import make_video
-    from unicorn_b200.tracker import QuasiDenseEmbedTracker
     from unicorn_b200.weights import make_state_dict
     name = "unicorn_track_tiny"
     sd = make_state_dict(name, 0)
-    cfg = orc.CONFIGS[name]
+    return name, sd, orc.CONFIGS[name], UnicornEngine(sd, name)
+
+
+def test_mot_ids_from_engine_embeddings_match_oracle_embeddings():
+    """The association chain that the embeddings drive — backbone -> deformable interaction with the previous frame -> embedding
+    upsample -> sampling at the box centres -> bi-softmax -> QuasiDenseEmbedTracker ids (mot_evaluator.py:1014-1045) — with the
+    SAME boxes on both sides (the moving objects of the synthetic video plus two static clutter boxes, fixed scores), so that the
+    only difference is bf16 engine embeddings vs fp32 oracle embeddings.  Seeded random weights still give appearance-dependent
+    embeddings, so these decisions are well conditioned: the ids must match bit for bit over the whole sequence."""
+    import tracker_oracle as to
+    import unicorn_oracle as orc
+    from unicorn_b200 import ops
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    name, sd, cfg, eng = _mot_models()
+    n_obj = 5
+    frames, boxes = make_video(N_FRAMES, 320, 320, seed=11, n_obj=n_obj)
+    clutter = torch.tensor([[8.0, 250.0, 60.0, 310.0], [250.0, 10.0, 310.0, 70.0]])
+    scores = torch.tensor([0.95, 0.9, 0.85, 0.82, 0.6, 0.3, 0.2])  # > init 0.8: tracks start; 0.6: matched only; < 0.5: backdrops
+    trk_e, trk_o = QuasiDenseEmbedTracker(), to.QDTrackerOracle()
+    prev_e = prev_o = None
+    img_dev = torch.empty(1, 3, 320, 320, device="cuda")
+    feats_dev = torch.zeros(16, 128, device="cuda")
+    mism, rows, sim_err = 0, 0, 0.0
+    for t in range(N_FRAMES):
+        bx = torch.cat([torch.cat([boxes[t], clutter]), scores[:, None]], 1)
+        # engine side
+        img_dev.copy_(frames[t:t + 1])
+        eng.begin_frame()
+        _, seq = eng.backbone(img_dev, tag="m%d" % (t & 1))
+        cur = seq["feat"].clone()
+        _, f_cur = eng.interaction(prev_e if prev_e is not None else cur, cur)
+        emb = eng.upsample(f_cur, "m.emb")
+        prev_e = cur
+        fe = ops.sample_embed(emb, bx[:, :4].cuda().contiguous(), bx.shape[0], 8.0, out=feats_dev)[:bx.shape[0]].cpu()
+        # oracle side
+        with torch.no_grad():
+            _, oseq = orc.forward_backbone(frames[t:t + 1], sd, cfg)
+            _, of_cur = orc.deform_interaction(prev_o if prev_o is not None else oseq, oseq, sd)
+            fo = to.sample_embeddings(orc.upsample_embed(of_cur, sd), bx[:, :4], (320, 320))
+            prev_o = oseq
+        sim_err = max(sim_err, ((fe - fo).abs().max() / fo.abs().max()).item())
+        be, _, ie = trk_e.match(bx.clone(), torch.ones(bx.shape[0]), fe, t + 1)
+        bo, _, io = trk_o.match(bx.clone(), torch.ones(bx.shape[0]), fo, t + 1)
+        assert torch.equal(be, bo)
+        rows += ie.numel()
+        mism += int((ie != io).sum())
+    REPORT["mot_same_boxes"] = dict(frames=N_FRAMES, rows=rows, id_mismatches=mism, tracks=int(trk_e.num_tracklets), max_embedding_rel_err=sim_err)
+    print("MOT ids, engine vs oracle embeddings on identical boxes:", REPORT["mot_same_boxes"])
+    _save()
+    assert mism == 0 and trk_e.num_tracklets == trk_o.num_tracklets, REPORT["mot_same_boxes"]
+
+
+def test_mot_end_to_end_flip_report():
+    """Raw end-to-end statistic (each side on ITS OWN detections): reported, loosely bounded.  With seeded random weights the detector
+    fires on noise (scores 0.02-0.07, a different box set every frame: ~65 short-lived ids in 32 frames on BOTH sides), so id
+    continuity is ill conditioned by construction; the well-conditioned halves are asserted exactly elsewhere (detections:
+    tests/test_whole_gpu.py, association on identical boxes: the test above, tracker on identical detections: tests/test_tracker_gpu.py)."""
+    import tracker_oracle as to
+    import unicorn_oracle as orc
+    from unicorn_b200.mot import UnicornMOTTracker
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    name, sd, cfg, eng = _mot_models()
     frames, _ = make_video(N_FRAMES, 320, 320, seed=5, n_obj=3)
     CONF, NMS, THR = 0.01, 0.7, 0.03
     kw = dict(init_score_thr=0.04, obj_score_thr=0.035)  # the reference's 0.8 / 0.5 scaled to the score range of seeded random weights
-    trk = UnicornMOTTracker(UnicornEngine(sd, name), (320, 320), conf=CONF, nms=NMS, score_thr=THR, tracker=QuasiDenseEmbedTracker(**kw))
+    trk = UnicornMOTTracker(eng, (320, 320), conf=CONF, nms=NMS, score_thr=THR, tracker=QuasiDenseEmbedTracker(**kw))
     otrk = to.QDTrackerOracle(**kw)
     prev, id_map, paired, flips, n_e, n_o = None, {}, 0, 0, 0, 0
     for t in range(N_FRAMES):
@@ -127,6 +186,5 @@ def test_mot_id_flip_rate():
                          distinct_engine_ids=len(id_map))
     print("MOT id flip report:", REPORT["mot"])
     _save()
-    assert paired > 0, REPORT["mot"]
-    assert flips <= 0.1 * paired, REPORT["mot"]
-    assert abs(n_e - n_o) <= max(3, 0.15 * n_o), REPORT["mot"]
+    assert paired > 0.7 * min(n_e, n_o), REPORT["mot"]            # the two sides track the same boxes ...
+    assert abs(n_e - n_o) <= max(3, 0.15 * n_o), REPORT["mot"]    # ... and the same number of them

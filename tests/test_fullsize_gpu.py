@@ -218,11 +218,18 @@ def test_vos_large_mask_3_objects_vs_oracle():
         report[oid]["mask_iou"] = float((mb & rb).sum() / max(1, (mb | rb).sum()))
         assert report[oid]["coarse"] < 6e-2 and report[oid]["score"] < 5e-2, report
     agree = float((seg == o_seg).mean())
-    print("large-mask VOS, 3 objects:", report, "label agreement", agree)
+    import numpy as np
+    o_soft = np.stack([np.asarray(o_res[o]["soft"], dtype=np.float32) for o in init])
+    chans = np.concatenate([np.prod(1 - o_soft, axis=0, keepdims=True), o_soft], 0)
+    top2 = np.sort(chans, axis=0)[-2:]
+    cond = (top2[1] - top2[0]) > 0.25  # pixels whose label is a well-conditioned argmax (seeded random weights: noise-like soft masks)
+    agree_cond = float((seg == o_seg)[cond].mean()) if cond.any() else 1.0
+    print("large-mask VOS, 3 objects:", report, "label agreement", agree, "where the oracle's margin > 0.25:", agree_cond, "fraction", float(cond.mean()))
+    assert agree_cond > 0.99
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
         import json
-        json.dump(dict(per_object=report, label_agreement=agree), open(os.path.join(out_dir, "r2_vos_large_parity.json"), "w"), indent=1)
+        json.dump(dict(per_object=report, label_agreement=agree, label_agreement_margin_0p25=agree_cond, margin_fraction=float(cond.mean())), open(os.path.join(out_dir, "r2_vos_large_parity.json"), "w"), indent=1)
     # where the engine picks the oracle's instance its mask must be the oracle's mask (bf16 features: IoU, not bit equality)
     for oid, rr in report.items():
         if rr["top1_iou"] > 0.9:
