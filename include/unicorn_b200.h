@@ -110,11 +110,13 @@ UC_API int uc_stem_ln(const void* img, int img_is_u8_hwc, const float* w48, cons
 UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias, const float* lnw, const float* lnb,
                          void* y_bf16, int B, int H, int W, int C, float eps, void* stream);
 
-/* Depthwise 7x7 (pad 3)+bias only (shared-memory tiled); follow with uc_layernorm for the ConvNeXt block. */
-/* ln_stats (optional, may be NULL): [B*H*W][2] int64 fixed point (value * 2^22), zeroed by the caller; receives the per-pixel
- * {sum, sum of squares} over C of the stored outputs, for a pwconv1 with the LayerNorm folded in (UcConv2d.row_stats). */
+/* Depthwise 7x7 (pad 3) + bias of the ConvNeXt block (convnext.py:43), TMA staged (csrc/dwconv_tma.cu); follow with uc_layernorm,
+ * or give ln_stats and fold the LayerNorm into pwconv1 (UcConv2d.row_stats).  x, y NHWC bf16 contiguous, not in place; w49 fp32 [49][C].
+ * ln_stats (optional, may be NULL): [B*H*W][2] int64 fixed point (value * 2^22), zeroed by the caller; receives the per-pixel
+ * {sum, sum of squares} over C of the stored outputs.  work_counter (optional, may be NULL): one device int, ZERO before the launch,
+ * used to hand out the tiles dynamically (balanced SM loads on small maps); NULL = static round-robin. */
 UC_API int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
-                      void* ln_stats, void* stream);
+                      void* ln_stats, int* work_counter, void* stream);
 
 /* Row LayerNorm: y[m,:] = LN(x[m,:] + res[m,:]) * w + b  (res may be NULL).  16-bit rows with element strides.
  * convnext.py:176-184 (downsample / out norms), deformable_transformer.py:113,121,127-130 (post-norm). */

@@ -59,6 +59,14 @@ def test_dwconv_tiled(C, H, W):
     out = ops.dwconv7(x, ops.pack_dw_weight(w), b)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=3, groups=C).permute(0, 2, 3, 1)
     close(out, ref, 5e-3, "dwconv tiled")
+    # tiles handed out by an atomic work counter (the engine's mode) instead of the static round-robin: same bits; and with the
+    # LayerNorm statistics: sum / sum of squares over C of the stored values, fixed point 2^22
+    st = torch.zeros(2 * H * W, 2, dtype=torch.int64, device=dev)
+    out2 = ops.dwconv7(x, ops.pack_dw_weight(w), b, ln_stats=st, work_counter=torch.zeros(1, dtype=torch.int32, device=dev))
+    assert torch.equal(out, out2)
+    of = out.float().reshape(-1, C).double()
+    assert torch.allclose(st[:, 0].double() / 4194304.0, of.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[:, 1].double() / 4194304.0, (of ** 2).sum(1), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("C", [96, 100, 192, 256, 384, 768, 1536, 2048])  # 100: not a multiple of 8 -> the 32-bit-access kernel

@@ -102,7 +102,7 @@ def test_vos_driver_vs_reference_class_golden():
     class's.  A pixel's label is an argmax over soft masks; with seeded random weights those are noise-like, so the comparison is
     margin aware: where the fp32 oracle's winning channel leads by more than MARGIN the engine must agree (>= 99 %), the raw
     agreement is reported and loosely bounded, and the engine's soft masks must stay within SOFT_TOL of the oracle's."""
-    MARGIN, SOFT_TOL = 0.25, 0.12
+    MARGIN, SOFT_TOL = 0.12, 0.12  # measured soft-mask drift p99 <= 0.036: the margin is > 3x that
     g, segs, states, softs = _run_driver(False, keep_soft=True)
     orc_frames = _oracle_softs(g)
     report = dict(raw_agreement=[], conditioned_agreement=[], conditioned_fraction=[], soft_err_p99=[], oracle_vs_reference=[])
@@ -112,7 +112,7 @@ def test_vos_driver_vs_reference_class_golden():
         top2 = np.sort(chans, axis=0)[-2:]
         cond = (top2[1] - top2[0]) > MARGIN
         report["raw_agreement"].append(float((s == r).mean()))
-        report["conditioned_agreement"].append(float((s == r)[cond].mean()))
+        report["conditioned_agreement"].append(float((s == r)[cond].mean()) if cond.any() else 1.0)
         report["conditioned_fraction"].append(float(cond.mean()))
         report["oracle_vs_reference"].append(float((o_seg == r).mean()))
         report["soft_err_p99"].append(float(np.percentile(np.abs(softs[t] - o_soft), 99)))

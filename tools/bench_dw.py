@@ -13,11 +13,15 @@ R = 20
 HBM = float(os.environ.get("UC_HBM_GBS", 6487.1))
 
 
+CTR = torch.zeros(R + 1, dtype=torch.int32, device=dev)  # one zeroed work counter per launch of a replay
+
+
 def timed(fn):
-    fn(); torch.cuda.synchronize()
+    CTR.zero_(); fn(R); torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        for _ in range(R): fn()
+        CTR.zero_()
+        for k in range(R): fn(k)
     g.replay(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); g.replay(); g.replay(); b.record(); torch.cuda.synchronize()
@@ -30,10 +34,11 @@ for name, H, W, C in SHAPES:
     b, lw, lb = (torch.randn(C, device=dev) for _ in range(3))
     y = torch.empty_like(x)
     st = torch.zeros(H * W, 2, dtype=torch.int64, device=dev)
-    t_dw = timed(lambda: ops.dwconv7(x, w, b, out=y))
-    t_st = timed(lambda: ops.dwconv7(x, w, b, out=y, ln_stats=st))
-    t_ln = timed(lambda: ops.layernorm(y.view(-1, C), lw, lb, 1e-6, out=y.view(-1, C)))
+    t_dw = timed(lambda k: ops.dwconv7(x, w, b, out=y, work_counter=CTR[k:k + 1]))
+    t_static = timed(lambda k: ops.dwconv7(x, w, b, out=y))
+    t_st = timed(lambda k: ops.dwconv7(x, w, b, out=y, ln_stats=st, work_counter=CTR[k:k + 1]))
+    t_ln = timed(lambda k: ops.layernorm(y.view(-1, C), lw, lb, 1e-6, out=y.view(-1, C)))
     byt = 4.0 * H * W * C  # algorithmic bytes: read + write the bf16 map once
     fl = 98.0 * H * W * C
     print(f"{name:7s} {H:4d}x{W:<4d} C={C:5d}  dwconv {t_dw:7.1f} us ({byt/t_dw/1e3:7.1f} GB/s = {byt/t_dw/1e3/HBM*100:5.1f}% HBM, {fl/t_dw/1e6:5.1f} TFLOP/s fp32)"
-          f"  +stats {t_st:7.1f} us  layernorm {t_ln:6.1f} us  tiled={os.environ.get('UC_DW_TILED', '0')}", flush=True)
+          f"  static-schedule {t_static:7.1f} us  +stats {t_st:7.1f} us  layernorm {t_ln:6.1f} us  tiled={os.environ.get('UC_DW_TILED', '0')}", flush=True)

@@ -76,7 +76,8 @@ class _Head:
             locs.append((torch.stack((xv, yv), 2).view(-1, 2).float() + 0.5) * STRIDES[k])  # unicorn_head_mask.py:518
             lvls.append(torch.full((1, h * w), k, device=d.device, dtype=torch.long))
         mf, um = e.mask_branch(fpn)
-        return out, torch.cat(locs, 0), dyn, torch.cat(lvls, 1), ops.nhwc_to_nchw(mf), ops.nhwc_to_nchw(um)
+        # mask-branch outputs are fp32 NHWC (ops.nhwc_to_nchw converts 16-bit maps): plain permutes at this compatibility boundary
+        return out, torch.cat(locs, 0), dyn, torch.cat(lvls, 1), mf.permute(0, 3, 1, 2).contiguous(), um.permute(0, 3, 1, 2).contiguous()
 
 
 class UnicornB200Model:

@@ -5,9 +5,10 @@
 // replaces the three materialising passes of external/lib/test/tracker/unicorn_sot.py:95-100
 // (torch.mm -> softmax(dim=0) -> values @ trans_mat; same in unicorn_vos.py:171-181): the (N_ref x N_cur) similarity
 // matrix (512 MB in fp16 at 800x1280) never leaves the SM.  Flash-attention style: one CTA owns 128 current positions
-// (rows of the TMEM accumulator), streams the reference positions in chunks of 128 through a TMA ring, computes the
-// 128x128 similarity tile with tcgen05.mma into a double-buffered TMEM accumulator, and four softmax warps (one
-// thread per current position, no cross-thread reductions) keep the running max / sum / weighted label sums.
+// (rows of the TMEM accumulator), streams the reference positions in chunks of 256 through a TMA ring, computes the
+// 128x256 similarity tile with tcgen05.mma (UMMA 128x256x16) into a double-buffered TMEM accumulator (all 512 columns), and
+// sixteen softmax warps (four per TMEM lane quadrant, 64 columns each, no cross-thread reductions inside the loop) keep the
+// running max / sum / weighted label sums; one exponential in four is evaluated on the FMA pipe (the kernel is MUFU bound).
 // V has only n_obj (1..8) rows, so the P.V product is done with CUDA-core FMAs on the probabilities instead of
 // wasting an MMA tile.
 #include "uc_ptx.cuh"
@@ -16,11 +17,15 @@
 
 namespace uc {
 
-constexpr int kCorrC = 128;      // embedding channels
-constexpr int kCorrTile = 128;   // current positions per CTA == reference positions per chunk
-constexpr int kCorrStages = 4;
-constexpr int kCorrTileBytes = kCorrTile * kCorrC * 2;  // 32 KB (two 128B-swizzled 64-channel halves)
-constexpr int kCorrSoftmaxWarps = 16;                  // 4 per TMEM lane quadrant, each owning 32 of the 128 chunk columns
+constexpr int kCorrC = 128;       // embedding channels
+constexpr int kCorrTile = 128;    // current positions per CTA (rows of the TMEM accumulator)
+constexpr int kCorrChunk = 256;   // reference positions per MMA chunk (UMMA N = 256: half as many barrier hand-offs as 128)
+constexpr int kCorrStages = 2;    // K ring (64 KB per stage)
+constexpr int kCorrVSlots = 6;    // label-value slots, see the producer: chunk x's values may be written once every softmax warp has LOADED
+                                  // S of chunk x-4 (it may still be computing chunk x-4, but is done with x-5): >= 5 slots are needed
+constexpr int kCorrQBytes = kCorrTile * kCorrC * 2;    // 32 KB (two 128B-swizzled 64-channel halves)
+constexpr int kCorrKBytes = kCorrChunk * kCorrC * 2;   // 64 KB
+constexpr int kCorrSoftmaxWarps = 16;                  // 4 per TMEM lane quadrant, each owning 64 of the 256 chunk columns
 constexpr int kCorrThreads = (2 + kCorrSoftmaxWarps) * 32;
 
 struct alignas(64) CorrParams {
@@ -36,15 +41,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, 2^f by a degree-4 minimax polynomial
+// (max relative error 2.9e-6 — below the bf16/fp16 rounding of the similarity itself), 2^n by an exponent-field add.  One element in
+// four takes this path: the kernel is bound by the MUFU unit (16 ex2 per clock per SM), the FMA pipe has room for ~25 % of them.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;              // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);        // in [-0.5, 0.5]
+  float p = fmaf(f, 9.582853e-3f, 5.5906426e-2f);  // weighted least-squares (near-minimax) fit on [-0.5, 0.5] with p(0) = 1
+  p = fmaf(p, f, 2.4024099e-1f);
+  p = fmaf(p, f, 6.9312418e-1f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 template <int NOBJ>
 __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_constant__ CorrParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + kCorrTileBytes;
-  float* sV = reinterpret_cast<float*>(sK + kCorrStages * kCorrTileBytes);  // [2][NOBJ][128]
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(sV + 2 * NOBJ * kCorrTile);
+  uint8_t* sK = smem + kCorrQBytes;
+  float* sV = reinterpret_cast<float*>(sK + kCorrStages * kCorrKBytes);  // [kCorrVSlots][NOBJ][256]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(sV + kCorrVSlots * NOBJ * kCorrChunk);
   uint64_t* k_full = q_full + 1;
   uint64_t* k_empty = k_full + kCorrStages;
   uint64_t* s_full = k_empty + kCorrStages;
@@ -53,18 +71,18 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * kCorrTile;
-  const int nchunks = (p.n_ref + kCorrTile - 1) / kCorrTile;
+  const int nchunks = (p.n_ref + kCorrChunk - 1) / kCorrChunk;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmQ);
     prefetch_tmap(&p.tmK);
     mbar_init(q_full, 1);
-    for (int i = 0; i < kCorrStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < kCorrStages; ++i) { mbar_init(&k_full[i], 2); mbar_init(&k_empty[i], 1); }  // full: TMA bytes + label values
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kCorrSoftmaxWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);  // two 128 x 256 fp32 similarity buffers
     tmem_relinquish();
   }
   tc_fence_before();
@@ -75,23 +93,36 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // TMA producer: converged warp, one elected lane issues (keeps addresses in uniform registers)
+    // Producer: TMA for the K chunk (one elected lane) and — all 32 lanes — the chunk's label values V[:, i0 .. i0+255] into their
+    // slot.  The producer runs up to kCorrStages chunks ahead of the MMA, so the L2 latency of these loads is never on the softmax
+    // warps' critical path (it was: they used to stage V themselves behind a 512-thread barrier every chunk).
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kCorrTileBytes);
+      mbar_arrive_expect_tx(q_full, kCorrQBytes);
       tma_load_2d(sQ, &p.tmQ, q_full, 0, j0);
-      tma_load_2d(sQ + kCorrTileBytes / 2, &p.tmQ, q_full, 64, j0);
+      tma_load_2d(sQ + kCorrQBytes / 2, &p.tmQ, q_full, 64, j0);
     }
     __syncwarp();
     int stage = 0, phase = 0;
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(&k_empty[stage], phase ^ 1);
+      const int i0 = c * kCorrChunk;
       if (elect_one()) {
-        mbar_arrive_expect_tx(&k_full[stage], kCorrTileBytes);
-        uint8_t* dst = sK + stage * kCorrTileBytes;
-        tma_load_2d(dst, &p.tmK, &k_full[stage], 0, c * kCorrTile);
-        tma_load_2d(dst + kCorrTileBytes / 2, &p.tmK, &k_full[stage], 64, c * kCorrTile);
+        mbar_arrive_expect_tx(&k_full[stage], kCorrKBytes);
+        uint8_t* dst = sK + stage * kCorrKBytes;
+        tma_load_2d(dst, &p.tmK, &k_full[stage], 0, i0);
+        tma_load_2d(dst + kCorrKBytes / 2, &p.tmK, &k_full[stage], 64, i0);
+      }
+      float* vb = sV + (c % kCorrVSlots) * NOBJ * kCorrChunk;
+#pragma unroll
+      for (int o = 0; o < NOBJ; ++o) {
+#pragma unroll
+        for (int t = 0; t < kCorrChunk / 32; ++t) {
+          const int i = i0 + t * 32 + lane;
+          vb[o * kCorrChunk + t * 32 + lane] = (o < p.n_obj && i < p.n_ref) ? __ldg(p.V + static_cast<long>(o) * p.ldv + i) : 0.f;
+        }
       }
       __syncwarp();
+      if (lane == 0) mbar_arrive(&k_full[stage]);  // release: the MMA warp acquires it, its commit publishes it to the softmax warps
       if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
@@ -106,11 +137,12 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
       mbar_wait(&k_full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t k_desc = k_desc0 + static_cast<uint64_t>((stage * kCorrTileBytes) >> 4);
+        const uint64_t k_desc = k_desc0 + static_cast<uint64_t>((stage * kCorrKBytes) >> 4);
 #pragma unroll
         for (int ks = 0; ks < kCorrC / 16; ++ks) {
-          const uint64_t o = static_cast<uint64_t>(((ks >> 2) * (kCorrTileBytes / 2) + (ks & 3) * 32) >> 4);
-          umma_f16(tmem_base + buf * kCorrTile, q_desc + o, k_desc + o, idesc, ks != 0 ? 1u : 0u);
+          const uint64_t qo = static_cast<uint64_t>(((ks >> 2) * (kCorrQBytes / 2) + (ks & 3) * 32) >> 4);
+          const uint64_t ko = static_cast<uint64_t>(((ks >> 2) * (kCorrKBytes / 2) + (ks & 3) * 32) >> 4);
+          umma_f16(tmem_base + buf * kCorrChunk, q_desc + qo, k_desc + ko, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[stage]);
         umma_commit(&s_full[buf]);
@@ -120,81 +152,91 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
     }
   } else {
     // ---------------- online softmax + label propagation
-    // 16 warps: warp w owns TMEM lane quadrant (w & 3) (= 32 current positions) and columns [32*cg, 32*cg+32) of every
-    // 128-column similarity chunk, cg = (w-2)/4.  Each thread keeps a private running (max, sum, weighted label sums)
-    // for its (position, column group); the four partial states of a position are merged once at the end.  Four warps
-    // per scheduler hide the tcgen05.ld / MUFU latencies that a single warp per scheduler could not.
+    // 16 warps: warp w owns TMEM lane quadrant (w & 3) (= 32 current positions) and columns [64*cg, 64*cg+64) of every 256-column
+    // similarity chunk, cg = (w-2)/4.  Each thread keeps a private running (max, sum, weighted label sums) for its (position,
+    // column group); the four partial states of a position are merged once at the end.  No block-level barrier inside the loop: the
+    // warps drift apart and hide one another's tcgen05.ld / MUFU latencies.  Everything is in the log2 domain: p = 2^(s*log2e - m).
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int tid = threadIdx.x - 64;  // 0..511 among the softmax threads
     const int j = j0 + row;
     constexpr float kLog2e = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
-    float acc[NOBJ];
+    constexpr int CW = kCorrChunk / 4;  // 64 columns per warp and chunk
+    float m = -INFINITY;
+    float l[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[NOBJ][2];
 #pragma unroll
-    for (int o = 0; o < NOBJ; ++o) acc[o] = 0.f;
+    for (int o = 0; o < NOBJ; ++o) acc[o][0] = acc[o][1] = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
-      const int i0 = c * kCorrTile;
-      float* vb = sV + buf * NOBJ * kCorrTile;
-      if (tid < kCorrTile) {
-#pragma unroll
-        for (int o = 0; o < NOBJ; ++o) {
-          float v = 0.f;
-          if (o < p.n_obj && i0 + tid < p.n_ref) v = __ldg(p.V + static_cast<long>(o) * p.ldv + i0 + tid);
-          vb[o * kCorrTile + tid] = v;
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kCorrSoftmaxWarps * 32) : "memory");
+      const int i0 = c * kCorrChunk;
+      const float* vb = sV + (c % kCorrVSlots) * NOBJ * kCorrChunk;
       mbar_wait(&s_full[buf], (c >> 1) & 1);
       tc_fence_after();
-      const int nvalid = min(kCorrTile, p.n_ref - i0);
-      const int c0 = cg * 32;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrTile + c0, v);
-      tmem_ld_wait();
+      const int nvalid = min(kCorrChunk, p.n_ref - i0);
+      const int c0 = cg * CW;
+      uint32_t v[CW];
+      {
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrChunk + c0;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(ta, v0);
+        tmem_ld_32x32(ta + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) { v[t] = v0[t]; v[32 + t] = v1[t]; }
+      }
       // this warp's only read of the S buffer is done: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[buf]);
       if (c0 >= nvalid) continue;  // warp-uniform: fully masked column group of the tail chunk
-      float s[32];
-      float cmax = -INFINITY;
+      float s[CW];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) s[t] = __uint_as_float(v[t]) * kLog2e;
-      if (nvalid < kCorrTile) {  // tail chunk only (warp-uniform)
+      for (int t = 0; t < CW; ++t) s[t] = __uint_as_float(v[t]);
+      if (nvalid < kCorrChunk) {  // tail chunk only (warp-uniform)
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
+        for (int t = 0; t < CW; ++t)
           if (c0 + t >= nvalid) s[t] = -INFINITY;
       }
+      float mx[8];  // tree maximum (a 64-deep dependent chain of FMNMX would sit on the critical path of every chunk)
 #pragma unroll
-      for (int t = 0; t < 32; ++t) cmax = fmaxf(cmax, s[t]);
-      const float m_new = fmaxf(m, cmax);
-      const float scale = fast_exp2(m - m_new);
-      m = m_new;
-      l *= scale;
+      for (int t = 0; t < 8; ++t) mx[t] = fmaxf(fmaxf(s[t], s[t + 8]), fmaxf(s[t + 16], s[t + 24]));
 #pragma unroll
-      for (int o = 0; o < NOBJ; ++o) acc[o] *= scale;
+      for (int t = 0; t < 8; ++t) mx[t] = fmaxf(mx[t], fmaxf(fmaxf(s[t + 32], s[t + 40]), fmaxf(s[t + 48], s[t + 56])));
+      const float cmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      const float m_new = fmaxf(m, cmax * kLog2e);
+      if (m_new != m) {  // the running maximum moves in the first few chunks only: skip the rescale otherwise
+        const float scale = fast_exp2(m - m_new);
+        m = m_new;
 #pragma unroll
-      for (int t = 0; t < 32; t += 4) {
+        for (int u = 0; u < 4; ++u) l[u] *= scale;
+#pragma unroll
+        for (int o = 0; o < NOBJ; ++o) { acc[o][0] *= scale; acc[o][1] *= scale; }
+      }
+      const float neg_m = -m_new;
+#pragma unroll
+      for (int t = 0; t < CW; t += 4) {
         float pr[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { pr[u] = fast_exp2(s[t + u] - m_new); l += pr[u]; }
+        for (int u = 0; u < 4; ++u) {
+          const float x = fmaf(s[t + u], kLog2e, neg_m);  // <= 0 (-inf for masked columns -> p = 0 on both paths)
+          pr[u] = (u == 3) ? poly_exp2(x) : fast_exp2(x);
+          l[u] += pr[u];
+        }
 #pragma unroll
         for (int o = 0; o < NOBJ; ++o) {
-          const float4 vv = *reinterpret_cast<const float4*>(vb + o * kCorrTile + c0 + t);
-          acc[o] = fmaf(pr[0], vv.x, acc[o]); acc[o] = fmaf(pr[1], vv.y, acc[o]);
-          acc[o] = fmaf(pr[2], vv.z, acc[o]); acc[o] = fmaf(pr[3], vv.w, acc[o]);
+          const float4 vv = *reinterpret_cast<const float4*>(vb + o * kCorrChunk + c0 + t);  // same address in every lane: broadcast
+          acc[o][0] = fmaf(pr[0], vv.x, acc[o][0]); acc[o][1] = fmaf(pr[1], vv.y, acc[o][1]);
+          acc[o][0] = fmaf(pr[2], vv.z, acc[o][0]); acc[o][1] = fmaf(pr[3], vv.w, acc[o][1]);
         }
       }
     }
     // merge the four column groups of every position (the K ring is idle now: reuse it as scratch)
     float* part = reinterpret_cast<float*>(sK);  // [4][128][2 + NOBJ]
     float* mine = part + (cg * kCorrTile + row) * (2 + NOBJ);
-    mine[0] = m; mine[1] = l;
+    mine[0] = m; mine[1] = (l[0] + l[1]) + (l[2] + l[3]);
 #pragma unroll
-    for (int o = 0; o < NOBJ; ++o) mine[2 + o] = acc[o];
+    for (int o = 0; o < NOBJ; ++o) mine[2 + o] = acc[o][0] + acc[o][1];
     asm volatile("bar.sync 1, %0;" ::"n"(kCorrSoftmaxWarps * 32) : "memory");
     if (cg == 0 && j < p.n_cur) {
       float M = -INFINITY;
@@ -221,13 +263,13 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 template <int NOBJ>
 static int launch_corr(const CorrParams& p, int grid, cudaStream_t stream) {
-  constexpr int smem = (1 + kCorrStages) * kCorrTileBytes + 2 * NOBJ * kCorrTile * 4 + 256 + 1024;
+  constexpr int smem = kCorrQBytes + kCorrStages * kCorrKBytes + kCorrVSlots * NOBJ * kCorrChunk * 4 + 256 + 1024;
   static PerDeviceFlag attr_dev;
   bool& attr_set = attr_dev.get();
   if (!attr_set) {
@@ -266,12 +308,12 @@ extern "C" int uc_corr_propagate(const void* embed_ref, int ld_ref, int n_ref, c
   {
     uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(n_ref)};
     uint64_t strides[1] = {static_cast<uint64_t>(ld_ref) * 2};
-    uint32_t box[2] = {64, kCorrTile};
+    uint32_t box[2] = {64, kCorrChunk};
     rc = encode_tmap(&p.tmK, dt, 2, embed_ref, dims, strides, box);
     if (rc) return rc;
   }
   p.V = values; p.out = out; p.ldv = ldv; p.ldo = ldo; p.n_cur = n_cur; p.n_ref = n_ref; p.n_obj = n_obj;
-  p.idesc = umma_idesc_f16(dtype == UC_BF16 ? 1u : 0u, kCorrTile, kCorrTile);
+  p.idesc = umma_idesc_f16(dtype == UC_BF16 ? 1u : 0u, kCorrTile, kCorrChunk);
   const int grid = (n_cur + kCorrTile - 1) / kCorrTile;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (n_obj == 1) return launch_corr<1>(p, grid, stream);

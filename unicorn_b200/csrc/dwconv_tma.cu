@@ -2,16 +2,18 @@
 //
 //   y[b, oh, ow, c] = bias[c] + sum_{kh,kw} x[b, oh+kh-3, ow+kw-3, c] * w[kh*7+kw][c]          x, y NHWC bf16, w fp32 [49][C]
 //
-// Work item = a 16 x 4 output tile of one 64-channel chunk.  ONE elected thread asks the TMA engine for the item's
-// (16+6) x (4+6) x 64-channel input box — a 4-D box {64 ch, 22, 10, 1} of the NHWC map whose out-of-map part (the zero padding
-// of the convolution, negative coordinates included) is zero-filled by the hardware — and, when the chunk changed, for the
-// chunk's 49 x 64 fp32 filter taps; both land in shared memory and complete on one mbarrier.  No thread computes an address or
-// a bounds check for the staging.  256 threads = 8 warps; warp = one 8-pixel strip (half a tile row), lane = one channel pair:
-// 14 staged inputs and 8 packed (channel pair) accumulators live in registers, one packed FFMA2 per tap and pixel.
+// Work item = a 16 x 8 output tile of one 64-channel chunk.  ONE elected thread asks the TMA engine for the item's
+// (16+6) x (8+6) x 64-channel input box — a 4-D box {64 ch, 22, 14, 1} of the NHWC map whose out-of-map part (the zero padding
+// of the convolution, negative coordinates included) is zero-filled by the hardware — and for the chunk's 49 x 64 fp32 filter
+// taps; both land in one of TWO shared-memory stages and complete on that stage's mbarrier, so the box of item n+1 streams in
+// while item n is computed.  No thread computes an address or a bounds check for the staging.
 //
-// The kernel is bound by fp32 FMA issue (98 flop per output element, 15.6 GFLOP per 800x1280 frame), not by HBM: the grid is
-// persistent with four CTAs per SM (40.8 KB of shared memory each) so that the loads of one CTA overlap the arithmetic of the other
-// three, and the items are 64 pixels x 64 channels so that 148 x 4 CTAs stay balanced on maps as small as 50 x 80 (780 items).
+// The kernel is bound by fp32 FMA issue, not by HBM (98 flop per output element, 15.6 GFLOP per 800x1280 frame; measured peak of
+// packed FFMA2 with a shared multiplier operand: 73 TFLOP/s, tools/ubench/fma_rate.cu) — and at that rate the first version also
+// saturated the shared-memory pipe (0.5 wavefronts per FFMA2).  Register blocking brings that to 0.25: 256 threads = 8 warps;
+// a warp owns an 8-pixel strip of TWO output rows, a lane one channel pair; per staged input row (14 pixels, read and converted
+// once) it issues 2 x 56 FFMA2 — with filter row kh for the upper output row and the previous filter row, kept in registers, for the
+// lower one.  Items are handed out by an atomic counter (uneven per-SM loads of a static split cost 30 % on the 50 x 80 maps).
 //
 // Optional per-pixel LayerNorm statistics (sum, sum of squares over C of the STORED bf16 values, int64 fixed point 2^22, integer
 // atomics: order independent) feed the following pwconv1, which applies the normalisation in its epilogue (UcConv2d.row_stats).
@@ -23,142 +25,176 @@
 
 namespace uc {
 
-constexpr int kDwTW = 16, kDwTH = 4, kDwCCH = 64, kDwPX = 8;
-constexpr int kDwHW = kDwTW + 6, kDwHH = kDwTH + 6;               // 22 x 10 input box
+constexpr int kDwTW = 16, kDwTH = 8, kDwCCH = 64, kDwPX = 8, kDwR = 2;
+constexpr int kDwHW = kDwTW + 6, kDwHH = kDwTH + 6;               // 22 x 14 input box
 constexpr int kDwPixBytes = kDwCCH * 2;                             // 128 B per staged pixel
-constexpr int kDwTileBytes = kDwHH * kDwHW * kDwPixBytes;           // 28160
+constexpr int kDwTileBytes = kDwHH * kDwHW * kDwPixBytes;           // 39424
 constexpr int kDwWBytes = 49 * kDwCCH * 4;                          // 12544
-constexpr int kDwThreads = (kDwTW / kDwPX) * kDwTH * 32;            // 256
-constexpr int kDwSmem = kDwTileBytes + kDwWBytes + 128 + 128;       // + barrier + alignment slack
-constexpr int kDwCtasPerSm = 4;
+constexpr int kDwStageBytes = kDwTileBytes + kDwWBytes;             // 51968 (multiple of 128)
+constexpr int kDwThreads = (kDwTW / kDwPX) * (kDwTH / kDwR) * 32;   // 256
+constexpr int kDwSmem = 2 * kDwStageBytes + 128 + 128;              // two stages + barriers / item slots + alignment slack
+constexpr int kDwCtasPerSm = 2;
 
 struct alignas(64) DwParams {
   CUtensorMap tmX, tmW;
   const float* bias;
   uint16_t* y;
   unsigned long long* ln_stats;
+  int* work_counter;  // zeroed by the caller; nullptr = static round-robin
   int H, W, C, B, tiles_w, tiles_h, n_items;
 };
 
 __global__ void __launch_bounds__(kDwThreads, kDwCtasPerSm) dwconv7_tma_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ uint8_t dsm_raw[];
-  uint8_t* tile = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);  // 128-byte aligned; [10][22][64] bf16 (pointer stays a shared-memory pointer: LDS, not LD)
-  float* sw = reinterpret_cast<float*>(tile + kDwTileBytes);                                                   // [49][64] fp32
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tile + kDwTileBytes + kDwWBytes);
+  uint8_t* base = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);  // 128-byte aligned; the pointer stays a shared-memory pointer (LDS, not LD)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * kDwStageBytes);    // full[2]
+  volatile int* s_item = reinterpret_cast<volatile int*>(bar + 2);          // item index staged per stage (-1 = no more work)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hx = warp & 1, r = warp >> 1;  // this warp's strip: pixels 8 hx .. 8 hx + 7 of tile row r
+  const int hx = warp & 1, rp = warp >> 1;  // this warp's strip: pixels 8 hx .. 8 hx + 7 of tile rows 2 rp, 2 rp + 1
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tmX);
     prefetch_tmap(&p.tmW);
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
   pdl_wait();               // programmatic dependent launch: global memory is touched only after the predecessor completed
   pdl_launch_dependents();
-  // contiguous item range per CTA (chunk slowest): neighbouring tiles share their halo in L2 and mostly the filter chunk
-  const long n = p.n_items;
-  const int i0 = static_cast<int>(n * blockIdx.x / gridDim.x), i1 = static_cast<int>(n * (blockIdx.x + 1) / gridDim.x);
   const int tiles_img = p.tiles_w * p.tiles_h, tiles_chunk = tiles_img * p.B;
   const int C2 = p.C >> 1;
-  uint32_t phase = 0;
-  int last_chunk = -1;
-  for (int item = i0; item < i1; ++item) {
+  int static_next = blockIdx.x;  // thread 0 only
+
+  // thread 0: claim items (the atomic's round trip is hidden: an index is consumed one iteration after it was requested) and start
+  // the loads of an item into `stage` (the stage's previous readers are behind a __syncthreads)
+  auto fetch = [&]() {
+    if (p.work_counter) return atomicAdd(p.work_counter, 1);
+    const int item = static_next;
+    static_next += gridDim.x;
+    return item;
+  };
+  auto issue = [&](int stage, int item) {
+    if (item >= p.n_items) {
+      s_item[stage] = -1;
+      mbar_arrive(&bar[stage]);
+      return;
+    }
+    s_item[stage] = item;
     const int chunk = item / tiles_chunk, t = item - chunk * tiles_chunk;
     const int b = t / tiles_img, tt = t - b * tiles_img;
     const int oh0 = (tt / p.tiles_w) * kDwTH, ow0 = (tt % p.tiles_w) * kDwTW;
-    const int c0 = chunk * kDwCCH;
+    uint8_t* dst = base + stage * kDwStageBytes;
+    mbar_arrive_expect_tx(&bar[stage], kDwStageBytes);
+    tma_load_4d(dst, &p.tmX, &bar[stage], chunk * kDwCCH, ow0 - 3, oh0 - 3, b);
+    tma_load_2d(dst + kDwTileBytes, &p.tmW, &bar[stage], chunk * kDwCCH, 0);
+  };
+  int pending = 0;
+  if (threadIdx.x == 0) {
+    issue(0, fetch());
+    pending = fetch();
+  }
+  for (int it = 0;; ++it) {
+    const int stage = it & 1;
     if (threadIdx.x == 0) {
-      const bool load_w = chunk != last_chunk;
-      mbar_arrive_expect_tx(bar, kDwTileBytes + (load_w ? kDwWBytes : 0));
-      tma_load_4d(tile, &p.tmX, bar, c0, ow0 - 3, oh0 - 3, b);
-      if (load_w) tma_load_2d(sw, &p.tmW, bar, c0, 0);
-      last_chunk = chunk;
+      issue(stage ^ 1, pending);
+      pending = fetch();
     }
-    const int c = c0 + 2 * lane;  // this lane's channel pair (C is even: both channels are in range or neither)
+    mbar_wait(&bar[stage], (it >> 1) & 1);
+    const int item = s_item[stage];
+    if (item < 0) break;
+    const uint8_t* tile = base + stage * kDwStageBytes;                          // [14][22][64] bf16
+    const float* sw = reinterpret_cast<const float*>(tile + kDwTileBytes);      // [49][64] fp32
+    const int chunk = item / tiles_chunk, t = item - chunk * tiles_chunk;
+    const int b = t / tiles_img, tt = t - b * tiles_img;
+    const int oh0 = (tt / p.tiles_w) * kDwTH, ow0 = (tt % p.tiles_w) * kDwTW;
+    const int c = chunk * kDwCCH + 2 * lane;  // this lane's channel pair (C is even: both channels are in range or neither)
     const bool c_ok = c < p.C;
-    unsigned long long acc[kDwPX];
+    unsigned long long acc[kDwR][kDwPX];
     {
       const float2 bv = c_ok ? __ldg(reinterpret_cast<const float2*>(p.bias + c)) : make_float2(0.f, 0.f);
       const unsigned long long bb = (static_cast<unsigned long long>(__float_as_uint(bv.y)) << 32) | __float_as_uint(bv.x);
 #pragma unroll
-      for (int q = 0; q < kDwPX; ++q) acc[q] = bb;
+      for (int r = 0; r < kDwR; ++r)
+#pragma unroll
+        for (int q = 0; q < kDwPX; ++q) acc[r][q] = bb;
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-#pragma unroll 1
-    for (int kh = 0; kh < 7; ++kh) {
-      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + ((r + kh) * kDwHW + hx * kDwPX) * kDwPixBytes) + lane;
+    unsigned long long wprev[7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // input row 2 rp + i of the box: filter row i for output row 2 rp, filter row i - 1 for 2 rp + 1
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + ((kDwR * rp + i) * kDwHW + hx * kDwPX) * kDwPixBytes) + lane;
       unsigned long long v[kDwPX + 6];
 #pragma unroll
       for (int j = 0; j < kDwPX + 6; ++j) {
         const uint32_t u = rowp[j * (kDwPixBytes / 4)];
         v[j] = (static_cast<unsigned long long>(u & 0xffff0000u) << 32) | (u << 16);  // (lo -> .x, hi -> .y) as fp32 bits
       }
+      unsigned long long wcur[7];
+      if (i < 7) {
 #pragma unroll
-      for (int kw = 0; kw < 7; ++kw) {
-        const unsigned long long wv = *reinterpret_cast<const unsigned long long*>(sw + (kh * 7 + kw) * kDwCCH + 2 * lane);
+        for (int kw = 0; kw < 7; ++kw) wcur[kw] = *reinterpret_cast<const unsigned long long*>(sw + (i * 7 + kw) * kDwCCH + 2 * lane);
 #pragma unroll
-        for (int q = 0; q < kDwPX; ++q) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(v[q + kw]), "l"(wv));
+        for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+          for (int q = 0; q < kDwPX; ++q) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0][q]) : "l"(v[q + kw]), "l"(wcur[kw]));
+      }
+      if (i > 0) {
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+          for (int q = 0; q < kDwPX; ++q) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1][q]) : "l"(v[q + kw]), "l"(wprev[kw]));
+      }
+      if (i < 7) {
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) wprev[kw] = wcur[kw];
       }
     }
-    const int oh = oh0 + r;
-    uint32_t packed[kDwPX];
+    uint32_t packed[kDwR][kDwPX];
 #pragma unroll
-    for (int q = 0; q < kDwPX; ++q)
-      packed[q] = pack_bf16(__uint_as_float(static_cast<uint32_t>(acc[q] & 0xffffffffull)), __uint_as_float(static_cast<uint32_t>(acc[q] >> 32)));
-    if (oh < p.H && c_ok) {
-      uint32_t* yr = reinterpret_cast<uint32_t*>(p.y + (static_cast<long>(b) * p.H + oh) * p.W * p.C + c);
+    for (int r = 0; r < kDwR; ++r)
 #pragma unroll
-      for (int q = 0; q < kDwPX; ++q) {
-        const int ow = ow0 + hx * kDwPX + q;
-        if (ow < p.W) yr[static_cast<long>(ow) * C2] = packed[q];  // a warp writes the 128 contiguous bytes of one pixel's chunk
+      for (int q = 0; q < kDwPX; ++q)
+        packed[r][q] = pack_bf16(__uint_as_float(static_cast<uint32_t>(acc[r][q] & 0xffffffffull)), __uint_as_float(static_cast<uint32_t>(acc[r][q] >> 32)));
+#pragma unroll
+    for (int r = 0; r < kDwR; ++r) {
+      const int oh = oh0 + kDwR * rp + r;
+      if (oh < p.H && c_ok) {
+        uint32_t* yr = reinterpret_cast<uint32_t*>(p.y + (static_cast<long>(b) * p.H + oh) * p.W * p.C + c);
+#pragma unroll
+        for (int q = 0; q < kDwPX; ++q) {
+          const int ow = ow0 + hx * kDwPX + q;
+          if (ow < p.W) yr[static_cast<long>(ow) * C2] = packed[r][q];  // a warp writes the 128 contiguous bytes of one pixel's chunk
+        }
       }
     }
     if (p.ln_stats) {
-      // 16 values per lane (8 pixels x {sum, sumsq} of its channel pair) summed over the 32 lanes with a halving butterfly
-      // (16 shuffles instead of 80); lane 2k and 2k+1 end up with the total of value k.  Lanes of out-of-range channels hold 0.
-      float a[16];
+      // 32 values per lane (2 rows x 8 pixels x {sum, sumsq} of its channel pair) summed over the 32 lanes with a halving butterfly
+      // (31 shuffles instead of 160): lane L ends up with the total of value L = stat * 16 + row * 8 + pixel.
+      float a[32];
 #pragma unroll
-      for (int q = 0; q < kDwPX; ++q) {
-        const float r0 = bf16lo(packed[q]), r1 = bf16hi(packed[q]);
-        a[q] = r0 + r1;
-        a[8 + q] = fmaf(r0, r0, r1 * r1);
-      }
-      float b8[8], b4[4], b2[2], b1;
+      for (int r = 0; r < kDwR; ++r)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 16;
-        const float recv = __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + 8], 16);
-        b8[i] = (up ? a[i + 8] : a[i]) + recv;
-      }
+        for (int q = 0; q < kDwPX; ++q) {
+          const float r0 = bf16lo(packed[r][q]), r1 = bf16hi(packed[r][q]);
+          a[r * 8 + q] = r0 + r1;
+          a[16 + r * 8 + q] = fmaf(r0, r0, r1 * r1);
+        }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float recv = __shfl_xor_sync(0xffffffffu, up ? b8[i] : b8[i + 4], 8);
-        b4[i] = (up ? b8[i + 4] : b8[i]) + recv;
-      }
+      for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = lane & half;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
-        const float recv = __shfl_xor_sync(0xffffffffu, up ? b4[i] : b4[i + 2], 4);
-        b2[i] = (up ? b4[i + 2] : b4[i]) + recv;
+        for (int i = 0; i < half; ++i) {
+          const float recv = __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + half], half);
+          a[i] = (up ? a[i + half] : a[i]) + recv;
+        }
       }
-      {
-        const bool up = lane & 2;
-        const float recv = __shfl_xor_sync(0xffffffffu, up ? b2[0] : b2[1], 2);
-        b1 = (up ? b2[1] : b2[0]) + recv;
-      }
-      b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-      // value index held by this lane: bit 3 <- lane bit 4, bit 2 <- lane bit 3, bit 1 <- lane bit 2, bit 0 <- lane bit 1
-      const int k = (lane >> 1) & 15;
-      const int q = k & 7, ow = ow0 + hx * kDwPX + q;
-      if ((lane & 1) == 0 && oh < p.H && ow < p.W) {
-        unsigned long long* dst = p.ln_stats + ((static_cast<long>(b) * p.H + oh) * p.W + ow) * 2 + (k >> 3);
-        atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(b1 * kGnFixedScale)));
+      const int q = lane & 7, r = (lane >> 3) & 1, stat = lane >> 4;
+      const int oh = oh0 + kDwR * rp + r, ow = ow0 + hx * kDwPX + q;
+      if (oh < p.H && ow < p.W) {
+        unsigned long long* dst = p.ln_stats + ((static_cast<long>(b) * p.H + oh) * p.W + ow) * 2 + stat;
+        atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(a[0] * kGnFixedScale)));
       }
     }
-    __syncthreads();  // every thread has read the staged box / taps: the next item's TMA may overwrite them
+    __syncthreads();  // every thread has read this stage: thread 0 may refill it (two iterations from now it is waited on again)
   }
 }
 
@@ -176,7 +212,7 @@ extern "C" int uc_dwconv7_tiled(const void* x_bf16, const float* w49, const floa
                                 void* ln_stats, void* stream_v);
 
 extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
-                          void* ln_stats, void* stream_v) {
+                          void* ln_stats, int* work_counter, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!x_bf16 || !w49 || !bias || !y_bf16) return set_error(UC_EINVAL, "uc_dwconv7: null pointer");
   if (x_bf16 == y_bf16) return set_error(UC_EINVAL, "uc_dwconv7: not an in-place operation");
@@ -205,6 +241,7 @@ extern "C" int uc_dwconv7(const void* x_bf16, const float* w49, const float* bia
   p.bias = bias;
   p.y = static_cast<uint16_t*>(y_bf16);
   p.ln_stats = static_cast<unsigned long long*>(ln_stats);
+  p.work_counter = work_counter;
   p.H = H; p.W = W; p.C = C; p.B = B;
   p.tiles_w = (W + kDwTW - 1) / kDwTW;
   p.tiles_h = (H + kDwTH - 1) / kDwTH;

@@ -56,6 +56,7 @@ class UnicornEngine:
         # the GEMM epilogue) — UNTESTED on a GPU (round-2 item); off unless asked for / UC_LN_FOLD=1
         self.ln_fold = bool(int(os.environ.get("UC_LN_FOLD", "0"))) if ln_fold is None else bool(ln_fold)
         self._row_arena, self._row_used = None, 0
+        self._ctr_arena, self._ctr_used = None, 0  # work counters of the dynamically scheduled kernels (zeroed by begin_frame)
         self.autotune = autotune
         self.load_tuning()
         self._load(state_dict)
@@ -251,6 +252,11 @@ class UnicornEngine:
         if self._row_arena is not None:
             self._row_arena.zero_()
         self._row_used = 0
+        if self._ctr_arena is None:
+            self._ctr_arena = torch.zeros(256, dtype=torch.int32, device=self.dev)
+        else:
+            self._ctr_arena.zero_()
+        self._ctr_used = 0
 
     def _row_stats(self, n_pix):
         """[n_pix, 2] int64 slice of the per-frame LayerNorm-statistics arena (zeroed by begin_frame, handed out in call order)."""
@@ -262,6 +268,13 @@ class UnicornEngine:
         s = self._row_arena[self._row_used:need]
         self._row_used = need
         return s
+
+    def _ctr(self):
+        """One zeroed int32 work counter (uc_dwconv7 hands out its tiles with it), in call order like the statistics slots."""
+        c = self._ctr_arena[self._ctr_used:self._ctr_used + 1]
+        self._ctr_used += 1
+        assert self._ctr_used <= self._ctr_arena.shape[0]
+        return c
 
     def _stats(self, groups):
         s = self._stats_arena[self._stats_used]
@@ -285,12 +298,12 @@ class UnicornEngine:
         # stage 3: 2.3x the instructions per output, 8 warps per SM) — see DESIGN.md 4.3.
         if self.ln_fold and C % 32 == 0:
             rs = self._row_stats(B * H * W)
-            t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), ln_stats=rs)
+            t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), ln_stats=rs, work_counter=self._ctr())
             hid = self.conv(t, bp["w1f"], 1, bias=bp["c1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)),
                             row_stats=rs, col_s=bp["s1"], row_eps=1e-6)
             self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
             return x
-        t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape))
+        t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
         hid = self.conv(t, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
         self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)

@@ -145,14 +145,16 @@ def dwconv7_ln(x, w49, bias, lnw, lnb, eps=1e-6, out=None):
     return out
 
 
-def dwconv7(x, w49, bias, out=None, ln_stats=None):
+def dwconv7(x, w49, bias, out=None, ln_stats=None, work_counter=None):
     B, H, W, C = x.shape
     assert x.is_contiguous() and x.dtype == torch.bfloat16
     if out is None:
         out = torch.empty_like(x)
     if ln_stats is not None:
         assert ln_stats.dtype == torch.int64 and ln_stats.is_contiguous() and ln_stats.numel() == B * H * W * 2
-    _lib.check(_L().uc_dwconv7(_p(x), _p(w49), _p(bias), _p(out), B, H, W, C, _p(ln_stats), _S()), "uc_dwconv7")
+    if work_counter is not None:
+        assert work_counter.dtype == torch.int32 and work_counter.numel() >= 1
+    _lib.check(_L().uc_dwconv7(_p(x), _p(w49), _p(bias), _p(out), B, H, W, C, _p(ln_stats), _p(work_counter), _S()), "uc_dwconv7")
     return out
 
 
@@ -247,6 +249,7 @@ def nchw_to_nhwc(x, dtype=torch.bfloat16, out=None):
 
 def nhwc_to_nchw(x):
     B, H, W, C = x.shape
+    assert x.dtype in (torch.bfloat16, torch.float16), "uc_nhwc_to_nchw_f32 converts 16-bit NHWC maps"
     out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
     _lib.check(_L().uc_nhwc_to_nchw_f32(_p(x), _nhwc_ld(x), _p(out), B, C, _l(H * W), _DT[x.dtype], _S()), "uc_nhwc_to_nchw_f32")
     return out
