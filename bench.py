@@ -313,6 +313,36 @@ def main():
     e1.record()
     sync_all()
     dt_dev = e0.elapsed_time(e1) / 1e3
+    # ---------------- same, two frames in flight (sot.py submit / collect: the frames of a sequence are independent, each runs on its
+    # own stream and engine context) — reported next to the sequential number, results are bit-identical (tests/test_engine_gpu.py)
+    pipe = UnicornSOTTrack(eng, (H, W), use_graph=True, depth=2)
+    pipe.initialize_tensor(frames_u8[0:1], boxes[0, 0])
+    for i in range(4):
+        pipe.track_tensor(host_frames[i % len(host_frames)])
+    main = torch.cuda.current_stream()
+    sync_all()
+    e0.record()
+    for c in pipe._ctxs:
+        c.stream.wait_stream(main)
+    for i in range(K):
+        c = pipe._ctxs[i % 2]
+        with torch.cuda.stream(c.stream):
+            c.img_in_u8.copy_(dev_frames[i % len(dev_frames)], non_blocking=True)
+            c.graph.replay()
+    for c in pipe._ctxs:
+        main.wait_stream(c.stream)
+    e1.record()
+    sync_all()
+    dt_dev_pipe = e0.elapsed_time(e1) / 1e3
+    sync_all()
+    t0 = time.perf_counter()
+    pipe.submit(host_frames[0])
+    for i in range(1, K):
+        pipe.submit(host_frames[i % len(host_frames)])
+        pipe.collect()
+    pipe.collect()
+    torch.cuda.synchronize()
+    dt_e2e_pipe = time.perf_counter() - t0
     # ---------------- end to end through the public API with pinned host frames, driven by the product's multi-GPU module:
     # one sequence per rank (parallel.shard_sequences), start barrier, wall clock of the slowest rank, one all_gather of the
     # per-rank [frames, seconds, tracks] (parallel.gather_stats) — no data-path collective
@@ -384,12 +414,12 @@ def main():
 
     extra = {} if args.no_extra else extra_workloads(dev, rank, world, max(8, min(K, 24)), sync_all)
     if world > 1:
-        t = torch.tensor([dt_dev, dt_e2e] + [v for k in sorted(extra) for v in (extra[k]["_dt_dev"], extra[k]["_dt_e2e"])], device=dev, dtype=torch.float64)
+        t = torch.tensor([dt_dev, dt_e2e, dt_dev_pipe, dt_e2e_pipe] + [v for k in sorted(extra) for v in (extra[k]["_dt_dev"], extra[k]["_dt_e2e"])], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t = t.tolist()
-        dt_dev, dt_e2e = t[0], t[1]
+        dt_dev, dt_e2e, dt_dev_pipe, dt_e2e_pipe = t[0], t[1], t[2], t[3]
         for j, k in enumerate(sorted(extra)):
-            extra[k]["_dt_dev"], extra[k]["_dt_e2e"] = t[2 + 2 * j], t[3 + 2 * j]
+            extra[k]["_dt_dev"], extra[k]["_dt_e2e"] = t[4 + 2 * j], t[5 + 2 * j]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,6 +449,8 @@ def main():
                           "peak_source": pk["src"] + " bf16_tflops (burst)"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host_frames[0].numel() * host_frames[0].element_size()),
                 "d2h_bytes_per_step": int(trk.host_dets.numel() * 4 + 4)},
+        "pipelined_2_frames": {"value": world * K / dt_dev_pipe, "e2e": world * K / dt_e2e_pipe, "unit": "frames/s", "ms_per_step": 1e3 * dt_dev_pipe / K,
+                               "note": "two frames in flight on two streams (UnicornSOTTrack(depth=2).submit/collect); same results as the sequential tracker"},
         "multi_gpu": {"module": "unicorn_b200.parallel.run_sharded + gather_stats", "shard": sharded["shard"], "per_rank_frames_seconds_tracks": sharded["per_rank"]},
         "gpu_launches": launches_per_frame * K * 2,  # K device-resident steps + K end-to-end steps
         "launches_per_frame": launches_per_frame,

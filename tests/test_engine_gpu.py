@@ -158,3 +158,29 @@ def test_reference_api_facade(setup):
     assert whole.shape == (1, 2100, 5 + model.num_classes)
     with pytest.raises(ValueError):
         model(imgs=cur_img, mode="train")
+
+
+def test_pipelined_tracker_matches_sequential(setup):
+    """depth=2: two frames in flight on two streams / engine contexts (sot.py submit / collect).  The frames of a sequence are
+    independent, so every result must equal the sequential tracker's, bit for bit, in order."""
+    from unicorn_b200.sot import UnicornSOTTrack
+    from unicorn_b200.synthetic import make_video
+    trk = setup["trk"]
+    frames, boxes = make_video(8, 320, 320, seed=6)
+    host = [frames[i:i + 1].pin_memory() for i in range(8)]
+    seq = UnicornSOTTrack(trk.eng, (320, 320), use_graph=True)
+    seq.initialize_tensor(host[0], boxes[0, 0])
+    ref = [seq.track_tensor(host[i]) for i in range(1, 8)]
+    pipe = UnicornSOTTrack(trk.eng, (320, 320), use_graph=True, depth=2)
+    pipe.initialize_tensor(host[0], boxes[0, 0])
+    got = []
+    pipe.submit(host[1])
+    for i in range(2, 8):
+        pipe.submit(host[i])
+        got.append(pipe.collect())
+    got.append(pipe.collect())
+    for (d0, n0), (d1, n1) in zip(ref, got):
+        assert n0 == n1 and torch.equal(d0, d1)
+    # the synchronous call of a pipelined tracker is submit + collect
+    d, n = pipe.track_tensor(host[3])
+    assert n == ref[2][1] and torch.equal(d, ref[2][0])

@@ -61,6 +61,19 @@ class UnicornEngine:
         self.load_tuning()
         self._load(state_dict)
 
+    def fork(self):
+        """A second execution context on the SAME weights: its own activation buffers, statistics arenas and side streams, so that
+        two frames can be in flight on two streams (frames of a video are independent until association; see sot.py submit /
+        collect).  Packed weights, position tables and the tuning table are shared."""
+        import copy
+        ctx = copy.copy(self)
+        ctx._bufs = {}
+        ctx._stats_arena, ctx._stats_used = None, 0
+        ctx._row_arena, ctx._row_used = None, 0
+        ctx._ctr_arena, ctx._ctr_used = None, 0
+        ctx._side_streams, ctx._fork_stream = None, None
+        return ctx
+
     # ------------------------------------------------------------------------------------------ weights
     def _load(self, sd):
         dev = self.dev

@@ -36,9 +36,32 @@ def preprocess(img_rgb, input_size, out=None):
     return out, r
 
 
+class _Ctx:
+    """One frame in flight: an engine context (own activation buffers), static input buffers, NMS workspace, pinned result slot,
+    the captured CUDA graph and the stream it runs on."""
+
+    def __init__(self, eng, H, W, max_inst, stream):
+        dev = eng.dev
+        self.eng, self.stream = eng, stream
+        self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+        self.img_in_u8 = torch.empty(1, H, W, 3, dtype=torch.uint8, device=dev)
+        self.u8 = False
+        A = (H // 8) * (W // 8) + (H // 16) * (W // 16) + (H // 32) * (W // 32)
+        self.ws = ops.PostWorkspace(A, dev)
+        self.host_dets = torch.empty(max_inst, 7, dtype=torch.float32).pin_memory()
+        self.host_count = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.graph = None
+        self.event = torch.cuda.Event()
+        self.last = {}
+
+
 class UnicornSOTTrack:
     def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=3, use_graph=True, full_nms=False,
-                 device_preproc=False):
+                 device_preproc=False, depth=1):
+        """depth > 1: that many frames may be in flight (submit / collect), each on its own stream and engine context.  The frames
+        of a sequence are independent — the network never sees the previous frame's result (unicorn_sot.py:57-109 uses only the
+        initial frame's features and label map) — so overlapping them changes no output, only fills the SMs that one frame's
+        small kernels and launch gaps leave idle.  track() / track_tensor() stay synchronous (one frame in, its result out)."""
         self.eng, self.input_size = engine, tuple(input_size)
         self.confthre, self.nmsthre, self.max_inst = conf, nms, max_inst
         self.num_classes = 1
@@ -51,45 +74,52 @@ class UnicornSOTTrack:
         # full_nms=True reproduces the complete postprocess() list (used by the parity tests).
         self.nms_keep = 0 if full_nms else max_inst
         H, W = self.input_size
-        dev = engine.dev
-        self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
-        self.img_in_u8 = torch.empty(1, H, W, 3, dtype=torch.uint8, device=dev)
-        self._u8 = False
-        A = (H // 8) * (W // 8) + (H // 16) * (W // 16) + (H // 32) * (W // 32)
-        self.ws = ops.PostWorkspace(A, dev)
-        self.host_dets = torch.empty(max_inst, 7, dtype=torch.float32).pin_memory()
-        self.host_count = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self.graph = None
+        assert depth >= 1
+        self.depth = depth
+        self._ctxs = [_Ctx(engine if i == 0 else engine.fork(), H, W, max_inst,
+                           None if depth == 1 else torch.cuda.Stream(device=engine.dev)) for i in range(depth)]
+        self._submitted = self._collected = 0
         self.state = None
         self.frame_id = 0
         self.launches_per_frame = 0
 
+    # attributes of the single-context tracker (tests / bench read them): context 0
+    img_in = property(lambda self: self._ctxs[0].img_in)
+    img_in_u8 = property(lambda self: self._ctxs[0].img_in_u8)
+    ws = property(lambda self: self._ctxs[0].ws)
+    host_dets = property(lambda self: self._ctxs[0].host_dets)
+    host_count = property(lambda self: self._ctxs[0].host_count)
+    graph = property(lambda self: self._ctxs[0].graph)
+    last = property(lambda self: self._ctxs[(max(self._collected, 1) - 1) % self.depth].last)
+
     # -------------------------------------------------------------------------------- device-side frame
-    def _frame(self):
-        e = self.eng
+    def _frame(self, c):
+        e = c.eng
         e.begin_frame()
         def correlate(seq):  # runs on a second stream while the neck runs on the main one
             f_pre, f_cur = e.interaction(self.ref_feat, seq["feat"], ref_proj=self.ref_proj)
             e_pre, e_cur = e.upsample(f_pre, "embp"), e.upsample(f_cur, "embc")
             return f_pre, f_cur, e_pre, e_cur, e.propagate(e_pre, e_cur, self.lbs_pre)
 
-        fpn, seq, (f_pre, f_cur, e_pre, e_cur, priors) = e.backbone(self.img_in_u8 if self._u8 else self.img_in, tag="cur", side=correlate)
+        fpn, seq, (f_pre, f_cur, e_pre, e_cur, priors) = e.backbone(c.img_in_u8 if c.u8 else c.img_in, tag="cur", side=correlate)
         out = e.head(fpn, priors, "sot")
-        ops.postprocess_device(out[0], 1, self.confthre, self.nmsthre, self.ws, max_keep=self.nms_keep)
-        self.last = dict(fpn=fpn, feat=seq["feat"], inter_pre=f_pre, inter_cur=f_cur, embed_pre=e_pre, embed_cur=e_cur, priors=priors, head=out)
+        ops.postprocess_device(out[0], 1, self.confthre, self.nmsthre, c.ws, max_keep=self.nms_keep)
+        c.last = dict(fpn=fpn, feat=seq["feat"], inter_pre=f_pre, inter_cur=f_cur, embed_pre=e_pre, embed_cur=e_cur, priors=priors, head=out)
 
-    def _stage_input(self, frame):
+    def _stage_input(self, frame, c=None):
         """fp32 [1,3,H,W] (PreprocessorX format) or uint8 [1,H,W,3] (letterboxed BGR frame, 4x fewer H2D bytes)."""
+        c = c or self._ctxs[0]
         u8 = frame.dtype == torch.uint8
-        if u8 != self._u8:
-            self._u8, self.graph = u8, None  # the captured graph reads one of the two static input buffers
-        (self.img_in_u8 if u8 else self.img_in).copy_(frame, non_blocking=True)
-        return self.img_in_u8 if u8 else self.img_in
+        if u8 != c.u8:
+            c.u8, c.graph = u8, None  # the captured graph reads one of the two static input buffers
+        (c.img_in_u8 if u8 else c.img_in).copy_(frame, non_blocking=True)
+        return c.img_in_u8 if u8 else c.img_in
 
     def initialize_tensor(self, ref_frame, init_box_xyxy):
         """ref_frame: preprocessed fp32 [1,3,H,W] or uint8 [1,H,W,3] (host or device); init box in resized-image coordinates."""
         e = self.eng
         H, W = self.input_size
+        torch.cuda.synchronize()
         inp = self._stage_input(ref_frame)
         e.begin_frame()
         _, seq = e.backbone(inp, tag="ref")
@@ -97,34 +127,68 @@ class UnicornSOTTrack:
         self.ref_proj = e.project_ref(self.ref_feat)  # this tracker's own copy (several trackers may share the engine)
         lab = get_label_map(init_box_xyxy, H, W, e.dev)
         self.lbs_pre = ops.bilinear(lab, H // 8, W // 8, 8.0, 8.0).reshape(1, -1).contiguous()
-        self.graph = None
-        self.frame_id = 0
+        for c in self._ctxs:
+            c.graph = None
+        self.frame_id = self._submitted = self._collected = 0
         torch.cuda.synchronize()
 
-    def track_tensor(self, cur_frame):
-        """cur_frame: preprocessed fp32 [1,3,H,W], ideally pinned host memory.  Returns (dets[:max_inst] cpu, count)."""
-        self.frame_id += 1
-        self._stage_input(cur_frame)
+    def _run(self, c, frame):
+        """Enqueue one frame on context c (current stream = c.stream when pipelined): input copy, graph replay (or eager launches),
+        asynchronous read-back of (count, top rows) into the context's pinned slot."""
+        self._stage_input(frame, c)
         if not self.use_graph:
-            self._frame()
-        elif self.graph is None:
-            self._frame()  # warm-up: allocates every buffer, sets kernel attributes
+            self._frame(c)
+        elif c.graph is None:
+            self._frame(c)  # warm-up: allocates every buffer, sets kernel attributes, plan-time autotuning
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             from . import _lib
             l0 = _lib.LAUNCHES
-            with torch.cuda.graph(g):
-                self._frame()
+            with torch.cuda.graph(g, stream=c.stream):
+                self._frame(c)
             self.launches_per_frame = _lib.LAUNCHES - l0  # kernels recorded in the graph (C-ABI launches only)
-            self.graph = g
-            self.graph.replay()
+            c.graph = g
+            c.graph.replay()
         else:
-            self.graph.replay()
-        self.host_count.copy_(self.ws.count, non_blocking=True)
-        self.host_dets.copy_(self.ws.dets[:self.max_inst], non_blocking=True)
+            c.graph.replay()
+        c.host_count.copy_(c.ws.count, non_blocking=True)
+        c.host_dets.copy_(c.ws.dets[:self.max_inst], non_blocking=True)
+
+    def track_tensor(self, cur_frame):
+        """cur_frame: preprocessed fp32 [1,3,H,W] or uint8 [1,H,W,3], ideally pinned host memory.  Returns (dets[:max_inst] cpu, count)."""
+        if self.depth > 1:
+            self.submit(cur_frame)
+            return self.collect()
+        self.frame_id += 1
+        self._submitted = self._collected = self.frame_id
+        c = self._ctxs[0]
+        self._run(c, cur_frame)
         torch.cuda.current_stream().synchronize()
-        n = int(self.host_count.item())
-        return self.host_dets[:min(n, self.max_inst)].clone(), n
+        n = int(c.host_count.item())
+        return c.host_dets[:min(n, self.max_inst)].clone(), n
+
+    def submit(self, cur_frame):
+        """Pipelined protocol: enqueue a frame (returns immediately); at most `depth` frames may be uncollected."""
+        assert self._submitted - self._collected < self.depth, "collect() a frame first"
+        c = self._ctxs[self._submitted % self.depth]
+        self._submitted += 1
+        self.frame_id = self._submitted
+        if c.stream is None:
+            self._run(c, cur_frame)
+            c.event.record()
+            return
+        with torch.cuda.stream(c.stream):
+            self._run(c, cur_frame)
+            c.event.record()
+
+    def collect(self):
+        """Result of the oldest submitted frame: (dets[:max_inst] cpu, count)."""
+        assert self._collected < self._submitted, "nothing submitted"
+        c = self._ctxs[self._collected % self.depth]
+        self._collected += 1
+        c.event.synchronize()
+        n = int(c.host_count.item())
+        return c.host_dets[:min(n, self.max_inst)].clone(), n
 
     # -------------------------------------------------------------------------------- reference protocol
     def _preprocess(self, image):
