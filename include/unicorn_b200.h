@@ -205,6 +205,12 @@ UC_API int uc_sample_embed(const void* embed, int ld, int h, int w, int C, int d
  * softmax_cols(F)) / 2 with F = E M^T, zeroed where labels differ (labels may be NULL).  workspace >= N*M+2N+2M floats. */
 UC_API int uc_bisoftmax(const float* det_embeds, const float* memo_embeds, int N, int M, int C, const float* det_labels,
                         const float* memo_labels, float* workspace, float* scores, void* stream);
+/* Greedy assignment of QuasiDenseEmbedTracker.match (unicorn/tracker/quasi_dense_embed_tracker.py:188-199) on the device: rows =
+ * detections in descending score order, scores f32 [N,M] from uc_bisoftmax, memo_ids int64 [M] (-1 = backdrop), det_scores f32
+ * (element stride ld_det: column 4 of the [N,5] box rows).  ids_out int64 [N]: the tracklet id, -2 (duplicate of a tracklet, dropped)
+ * or -1 (unmatched).  taken_ws: M bytes of scratch.  One CTA; torch.max tie-breaking (first maximum). */
+UC_API int uc_qd_assign(const float* scores, int N, int M, const long long* memo_ids, const float* det_scores, int ld_det, float match_thr,
+                        float obj_thr, float nms_conf_thr, long long* ids_out, uint8_t* taken_ws, void* stream);
 /* Pairwise IoU out[i,j] of xyxy f32 boxes with row strides.  plus_one = 0: torchvision.ops.box_iou
  * (quasi_dense_embed_tracker.py:80,146); plus_one = 1: cython_bbox.bbox_overlaps' inclusive-pixel convention
  * (unicorn/tracker/matching.py:65-68, ByteTrack). */

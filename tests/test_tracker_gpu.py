@@ -58,6 +58,34 @@ def test_qd_tracker_ids_match_reference():
         b, _, ids = trk.match(boxes, torch.ones(boxes.size(0)), feats, i + 1)
         assert np.array_equal(ids.numpy(), g[f"ids_{i}"]), (i, ids, g[f"ids_{i}"])
         assert np.allclose(b.numpy(), g[f"boxes_{i}"])
+    # the memo never leaves the device, the greedy assignment is a kernel (uc_qd_assign)
+    assert trk.t_emb.is_cuda and trk.t_box.is_cuda and all(t.is_cuda for bd in trk.backdrops for t in bd)
+    assert trk.num_tracklets == int(g["num_tracklets"])
+
+
+def test_qd_assign_kernel_matches_reference_loop():
+    """uc_qd_assign against the reference's loop (quasi_dense_embed_tracker.py:188-199) on random score matrices with ties, claimed
+    columns, backdrop columns and the three thresholds in play."""
+    from unicorn_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    for N, M in ((1, 1), (17, 5), (40, 90), (300, 700)):
+        sc = torch.rand(N, M, generator=g)
+        sc[sc < 0.3] = 0.0
+        sc[:, M // 3] = sc[:, 0]  # exact ties between columns: the first maximum wins
+        memo_ids = torch.randint(-1, 50, (M,), generator=g)
+        boxes = torch.rand(N, 5, generator=g)
+        ref, s2 = torch.full((N,), -1, dtype=torch.long), sc.clone()
+        for i in range(N):
+            conf, j = torch.max(s2[i], dim=0)
+            if conf > 0.5 and memo_ids[j] > -1:
+                if boxes[i, 4] > 0.5:
+                    ref[i] = memo_ids[j]
+                    s2[:i, j] = 0
+                    s2[i + 1:, j] = 0
+                elif conf > 0.6:
+                    ref[i] = -2
+        got = ops.qd_assign(sc.cuda().contiguous(), memo_ids.cuda(), boxes.cuda().contiguous(), 0.5, 0.5, 0.6).cpu()
+        assert torch.equal(got, ref), (N, M)
     assert trk.num_tracklets == int(g["num_tracklets"])
 
 

@@ -51,8 +51,22 @@ def test_qd_tracker_host_logic_matches_reference_golden(monkeypatch):
         s = (f.softmax(1) + f.softmax(0)) / 2
         return s * (ld[:, None] == lm[None, :]).float() if ld is not None else s
 
+    def qd_assign(scores, memo_ids, boxes5, match_thr, obj_thr, nms_conf_thr):  # the greedy loop uc_qd_assign runs on the device
+        sc, ids = scores.clone(), torch.full((scores.shape[0],), -1, dtype=torch.long)
+        for i in range(sc.shape[0]):
+            conf, j = torch.max(sc[i], dim=0)
+            if conf > match_thr and memo_ids[j] > -1:
+                if boxes5[i, 4] > obj_thr:
+                    ids[i] = memo_ids[j]
+                    sc[:i, j] = 0
+                    sc[i + 1:, j] = 0
+                elif conf > nms_conf_thr:
+                    ids[i] = -2
+        return ids
+
     monkeypatch.setattr(qd.ops, "box_iou", lambda a, b, plus_one=False: _iou_np(a, b, plus_one))
     monkeypatch.setattr(qd.ops, "bisoftmax", bisoftmax)
+    monkeypatch.setattr(qd.ops, "qd_assign", qd_assign)
     monkeypatch.setattr(qd, "assoc_stream", lambda d: None)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     g = np.load(os.path.join(ROOT, "tests", "golden", "qd_tracker.npz"))

@@ -106,6 +106,52 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float* __restrict__ 
   out[t] = inter / (area1 + area2 - inter);
 }
 
+
+// Greedy assignment of the quasi-dense tracker (unicorn/tracker/quasi_dense_embed_tracker.py:188-199): detections in descending
+// score order; row i takes its best memo column j (first maximum, like torch.max) if conf > match_thr and the column is a tracklet
+// (memo id > -1): with det score > obj_thr it gets the id and the column is zeroed for every other row, otherwise conf > nms_conf_thr
+// marks it -2.  Inherently sequential over rows (N <= a few hundred): one CTA, the column search is parallel.
+__global__ void __launch_bounds__(256) qd_assign_kernel(const float* __restrict__ scores, int N, int M, const long long* __restrict__ memo_ids,
+                                                         const float* __restrict__ det_scores, int lds, float match_thr, float obj_thr,
+                                                         float nms_conf_thr, long long* __restrict__ ids, uint8_t* __restrict__ taken) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  for (int j = threadIdx.x; j < M; j += blockDim.x) taken[j] = 0;
+  __syncthreads();
+  for (int i = 0; i < N; ++i) {
+    float best = -1.f;  // scores are >= 0
+    int bj = 0x7fffffff;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const float v = taken[j] ? 0.f : scores[static_cast<long>(i) * M + j];
+      if (v > best) { best = v; bj = j; }  // strict: the earliest index of this thread's stride wins ties
+    }
+    s_val[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bj;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const float v = s_val[threadIdx.x + o];
+        const int jj = s_idx[threadIdx.x + o];
+        if (v > s_val[threadIdx.x] || (v == s_val[threadIdx.x] && jj < s_idx[threadIdx.x])) { s_val[threadIdx.x] = v; s_idx[threadIdx.x] = jj; }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float conf = s_val[0];
+      const int j = s_idx[0];
+      long long id = -1;
+      if (M > 0 && conf > match_thr && memo_ids[j] > -1) {
+        if (det_scores[static_cast<long>(i) * lds] > obj_thr) { id = memo_ids[j]; taken[j] = 1; }
+        else if (conf > nms_conf_thr) id = -2;
+      }
+      ids[i] = id;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace uc
 
 using namespace uc;
@@ -139,4 +185,14 @@ extern "C" int uc_box_iou(const float* a, int lda, int N, const float* b, int ld
   if (!a || !b || !out || N < 1 || M < 1 || lda < 4 || ldb < 4) return set_error(UC_EINVAL, "uc_box_iou: bad arguments");
   launch_pdl(box_iou_kernel, static_cast<unsigned>((static_cast<long>(N) * M + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v), a, lda, N, b, ldb, M, out, plus_one ? 1.f : 0.f);
   return check_launch("uc_box_iou");
+}
+
+extern "C" int uc_qd_assign(const float* scores, int N, int M, const long long* memo_ids, const float* det_scores, int ld_det, float match_thr,
+                            float obj_thr, float nms_conf_thr, long long* ids_out, uint8_t* taken_ws, void* stream_v) {
+  if (N < 0 || M < 0 || (N > 0 && (!det_scores || !ids_out)) || (N > 0 && M > 0 && (!scores || !memo_ids || !taken_ws)))
+    return set_error(UC_EINVAL, "uc_qd_assign: bad arguments");
+  if (N == 0) return UC_OK;
+  launch_pdl(qd_assign_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream_v), scores, N, M, memo_ids, det_scores, ld_det, match_thr, obj_thr,
+             nms_conf_thr, ids_out, taken_ws);
+  return check_launch("uc_qd_assign");
 }

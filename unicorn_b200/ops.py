@@ -346,6 +346,18 @@ def bisoftmax(det_embeds, memo_embeds, det_labels=None, memo_labels=None):
     return scores
 
 
+def qd_assign(scores, memo_ids, boxes5, match_thr, obj_thr, nms_conf_thr):
+    """scores f32 [N,M] (device), memo_ids int64 [M], boxes5 f32 [N,5] (score in column 4) -> ids int64 [N] (device)."""
+    N, M = scores.shape
+    ids = torch.full((N,), -1, dtype=torch.int64, device=boxes5.device)
+    if N == 0:
+        return ids
+    taken = torch.empty(max(M, 1), dtype=torch.uint8, device=boxes5.device)
+    _lib.check(_L().uc_qd_assign(_p(scores), N, M, _p(memo_ids), _p(boxes5[:, 4]), boxes5.stride(0), _f(match_thr), _f(obj_thr), _f(nms_conf_thr),
+                                 _p(ids), _p(taken), _S()), "uc_qd_assign")
+    return ids
+
+
 def box_iou(a, b, plus_one=False):
     N, M = a.shape[0], b.shape[0]
     out = torch.empty(N, M, dtype=torch.float32, device=a.device)
