@@ -81,8 +81,7 @@ typedef struct UcConv2d {
   int ldy;
   int y_dtype;
   int block_n; /* 0 = auto; else force the N tile (16,32,64,96,128,192,256); +1000 (1128,1192,1256) = the
-                  cta_group::2 variant: an SM pair computes a 256 x N tile with one pair-MMA stream; +2000 = stream-K
-                  scheduling of the single-CTA kernel (see sk_workspace) */
+                  cta_group::2 variant: an SM pair computes a 256 x N tile with one pair-MMA stream */
   /* Optional GroupNorm statistics of the (pre-activation) output, accumulated per (image, group):
    * gn_stats[b][g] = {sum, sumsq} as int64 fixed point (value * 2^22; integer atomics => order independent,
    * bit-reproducible); must be zeroed by the caller; NULL = off.  Consumed by uc_groupnorm_apply. */
@@ -94,13 +93,6 @@ typedef struct UcConv2d {
   const void* row_stats;
   const float* col_s;
   float row_eps;
-  /* Optional stream-K scheduling (block_n + 2000, e.g. 2192): the (tile, K-iteration) units are split evenly over one CTA per SM;
-   * tiles cut by a range boundary are reduced through this workspace by whichever CTA finishes last (fixed summation order:
-   * deterministic; nobody waits, so concurrent launches on other streams are safe — each needs its OWN workspace).  Size:
-   * 2 * #SMs * 128 * N_tile * 4 + #tiles * 4 bytes (uc_conv2d checks); the LAST #tiles ints must be zero before the first use
-   * (the kernel leaves them zero).  32-byte aligned.  NULL = off. */
-  void* sk_workspace;
-  long sk_workspace_bytes;
 } UcConv2d;
 UC_API int uc_conv2d(const UcConv2d* d, void* stream);
 

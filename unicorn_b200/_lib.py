@@ -25,7 +25,6 @@ class UcConv2d(ctypes.Structure):
         ("block_n", ctypes.c_int),
         ("gn_stats", ctypes.c_void_p), ("gn_groups", ctypes.c_int),
         ("row_stats", ctypes.c_void_p), ("col_s", ctypes.c_void_p), ("row_eps", ctypes.c_float),
-        ("sk_workspace", ctypes.c_void_p), ("sk_workspace_bytes", ctypes.c_long),
     ]
 
 

@@ -54,8 +54,6 @@ struct alignas(64) ConvKernelParams {
   const long long* row_stats;  // LayerNorm folded into this 1x1 conv: per input pixel {sum, sumsq} (fixed point 2^22) ...
   const float* col_s;          // ... column sums of the folded weights, channel count and epsilon of the LayerNorm
   float row_inv, row_eps;  // row_inv = 1 / (2^22 * Cin)
-  float* sk_ws;         // stream-K: [2 * grid][128 x BLOCK_N] fp32 partial accumulators (a CTA has at most two partial tiles) ...
-  int* sk_flags;        // ... and one arrival counter per tile (0 between launches)
   long long* gn_stats;  // fixed-point (2^22) accumulators: order-independent, hence deterministic
   int gn_groups, gn_gs;  // gs = Cout / groups
 };
@@ -164,7 +162,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  volatile int* sk_last = reinterpret_cast<volatile int*>(tmem_slot + 1);  // stream-K: "this CTA arrived last at the tile"
   // per-CTA GroupNorm accumulators (fixed point): the epilogue warps add into shared memory, ONE global atomic per group and
   // tile follows — the short-K GN convs were bound by ~36k global atomics on the 32 addresses of an image
   unsigned long long* gn_acc = reinterpret_cast<unsigned long long*>(smem + STAGES * (kABytes + B_BYTES) + 256);
@@ -175,34 +172,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   // work items: (N tile, group of CLUSTER consecutive M tiles); this CTA takes M tile group*CLUSTER + crank
   const int num_items = p.n_tiles * ((p.m_tiles + CLUSTER - 1) / CLUSTER);
   const int item0 = blockIdx.x / CLUSTER, item_step = gridDim.x / CLUSTER;
-  // ---- work decomposition.  Data parallel: this CTA walks whole tiles item0, item0 + item_step, ...  Stream-K (p.sk_ws, CLUSTER == 1):
-  // the (tile, K-iteration) units are cut into gridDim.x equal contiguous ranges, so every SM issues the same number of MMAs whatever
-  // the tile count (128 tiles on 148 SMs otherwise idle 14 % of the machine).  A range is a list of segments (tile, k0, k1); a
-  // segment that does not cover its tile's whole K range is PARTIAL: its fp32 accumulator goes to a workspace slot, then the tile's
-  // arrival counter is incremented; the CTA that arrives LAST sums all the tile's slots in CTA order (a fixed order: deterministic)
-  // and runs the fused epilogue.  Nobody ever waits for another CTA, so concurrent kernels on other streams cannot deadlock it.
-  const bool sk = CLUSTER == 1 && p.sk_ws != nullptr;
-  int nseg, sk_ia = 0, sk_ka = 0, sk_kb = 0;
-  long sk_u0 = 0;
-  const long sk_units = static_cast<long>(num_items) * kiters;
-  if (sk) {
-    sk_u0 = sk_units * blockIdx.x / gridDim.x;
-    const long u1 = sk_units * (blockIdx.x + 1) / gridDim.x;
-    sk_ia = static_cast<int>(sk_u0 / kiters);
-    sk_ka = static_cast<int>(sk_u0 - static_cast<long>(sk_ia) * kiters);
-    const int ib = static_cast<int>((u1 - 1) / kiters);
-    sk_kb = static_cast<int>((u1 - 1) - static_cast<long>(ib) * kiters) + 1;
-    nseg = u1 > sk_u0 ? ib - sk_ia + 1 : 0;
-  } else {
-    nseg = item0 < num_items ? (num_items - item0 + item_step - 1) / item_step : 0;
-  }
-  auto seg_at = [&](int i, int& item, int& k0, int& k1) -> bool {  // returns true for a partial segment
-    if (!sk) { item = item0 + i * item_step; k0 = 0; k1 = kiters; return false; }
-    item = sk_ia + i;
-    k0 = i == 0 ? sk_ka : 0;
-    k1 = i == nseg - 1 ? sk_kb : kiters;
-    return k0 != 0 || k1 != kiters;
-  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -235,36 +204,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 0) {
     // ---------------- TMA producer: the whole warp walks the loop (converged), one elected lane issues
     int stage = 0, phase = 0;
-    for (int si = 0; si < nseg; ++si) {
-      int item, k0, k1;
-      seg_at(si, item, k0, k1);
+    for (int item = item0; item < num_items; item += item_step) {
       const int n0 = (item % p.n_tiles) * BLOCK_N;
       const int mt = (item / p.n_tiles) * CLUSTER + crank;
       const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
       const int b = mt / (p.tiles_w * p.tiles_h);
-      int t = k0 / p.kchunks, kc = k0 - t * p.kchunks;
-      for (int it = k0; it < k1; ++it) {
+      for (int t = 0; t < p.ntaps; ++t) {
         const ConvTap tp = p.taps[t];
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (elect_one()) {
-          if (CLUSTER > 1 && p.debug == 2) {
-            if (crank == 0) mbar_arrive(&full[stage]);
-          } else if (CLUSTER > 1) {
-            // the leader arms its barrier for the bytes of both CTAs; the peer's loads are credited to it as well
-            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + B_BYTES));
-            tma_load_4d_2sm(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
-            tma_load_3d_2sm(sB + stage * B_BYTES, &p.tmBh, &full[stage], kc * kBlockK, tp.tap, n0 + crank * (BLOCK_N / 2));
-          } else if (p.debug == 2) {
-            mbar_arrive(&full[stage]);
-          } else {
-            mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
-            tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
-            tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (CLUSTER > 1 && p.debug == 2) {
+              if (crank == 0) mbar_arrive(&full[stage]);
+            } else if (CLUSTER > 1) {
+              // the leader arms its barrier for the bytes of both CTAs; the peer's loads are credited to it as well
+              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + B_BYTES));
+              tma_load_4d_2sm(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+              tma_load_3d_2sm(sB + stage * B_BYTES, &p.tmBh, &full[stage], kc * kBlockK, tp.tap, n0 + crank * (BLOCK_N / 2));
+            } else if (p.debug == 2) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], kABytes + B_BYTES);
+              tma_load_4d(sA + stage * kABytes, &p.tmA[tp.map], &full[stage], kc * kBlockK, ow0 + tp.dw, oh0 + tp.dh, b);
+              tma_load_3d(sB + stage * B_BYTES, &p.tmB, &full[stage], kc * kBlockK, tp.tap, n0);
+            }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        if (++kc == p.kchunks) { kc = 0; ++t; }
       }
     }
   } else if (warp == 1) {
@@ -274,19 +241,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t idesc = p.idesc;
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA)), b_desc0 = umma_desc_sw128(smem_u32(sB));
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int si = 0; si < nseg; ++si) {
-        int item, k0, k1;
-        seg_at(si, item, k0, k1);
+      for (int item = item0; item < num_items; item += item_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int it = k0; it < k1; ++it) {
+        for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (CLUSTER == 1 && p.debug == 1) {
             if (elect_one()) {
               mbar_arrive(&empty[stage]);
-              if (it == k1 - 1) mbar_arrive(&tmem_full[acc]);
+              if (it == kiters - 1) mbar_arrive(&tmem_full[acc]);
             }
           } else if (elect_one()) {
             // descriptor start address is in 16-byte units: stage offsets and the 32-byte K step are plain adds
@@ -294,13 +259,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
-              if (CLUSTER > 1) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it != k0 || k != 0) ? 1u : 0u);
-              else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it != k0 || k != 0) ? 1u : 0u);
+              if (CLUSTER > 1) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
             }
             // frees this smem stage (in both CTAs of the pair) when the MMAs above have read it
             if (CLUSTER > 1) umma_commit_2sm_mc(&empty[stage], static_cast<uint16_t>(0x3));
             else umma_commit(&empty[stage]);
-            if (it == k1 - 1) {  // accumulator (of this segment) complete (in both CTAs' tensor memory)
+            if (it == kiters - 1) {  // accumulator complete (in both CTAs' tensor memory)
               if (CLUSTER > 1) umma_commit_2sm_mc(&tmem_full[acc], static_cast<uint16_t>(0x3));
               else umma_commit(&tmem_full[acc]);
             }
@@ -326,10 +291,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const bool f16 = p.y_dtype == UC_F16;
     constexpr int ROUNDS = (BLOCK_N + 63) / 64;
     int acc = 0, acc_phase = 0, gpar = 0;
-    const int et = static_cast<int>(threadIdx.x) - 64;  // 0 .. 511 over the epilogue warps
-    for (int si = 0; si < nseg; ++si) {
-      int item, sk_k0, sk_k1;
-      const bool partial = seg_at(si, item, sk_k0, sk_k1);
+    for (int item = item0; item < num_items; item += item_step) {
       const int n0 = (item % p.n_tiles) * BLOCK_N;
       const int mt = (item / p.n_tiles) * CLUSTER + crank;
       const int ow0 = (mt % p.tiles_w) * p.tile_w, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.tile_h;
@@ -353,76 +315,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-      int sk_g0 = 0, sk_g1 = -1;  // partial tile: the CTAs sk_g0 .. sk_g1 hold its parts
-      if (partial) {
-        // ---- stream-K partial segment: raw fp32 accumulator -> this CTA's slot (slot 0: the segment is the first of the range, 1: not)
-        float* slot = p.sk_ws + ((static_cast<size_t>(blockIdx.x) * 2 + (si == 0 ? 0 : 1)) * kBlockM + row) * BLOCK_N;
-#pragma unroll 1
-        for (int rd = 0; rd <= last_rd; ++rd) {
-          const int c0 = rd * 64 + cg * 16;
-          uint32_t v[16];
-          tmem_ld_32x16(t_acc + c0, v);
-          tmem_ld_wait();
-          if (rd == last_rd) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          stg_v8(slot + c0, v);
-          stg_v8(slot + c0 + 8, v + 8);
-        }
-        if (last_rd < 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        // which CTAs share this tile (their ranges are contiguous and ordered)
-        const long tile_start = static_cast<long>(item) * kiters, tile_end = tile_start + kiters;
-        sk_g0 = static_cast<int>(blockIdx.x);
-        while (sk_g0 > 0 && sk_units * sk_g0 / static_cast<long>(gridDim.x) > tile_start) --sk_g0;
-        sk_g1 = static_cast<int>(blockIdx.x);
-        while (sk_g1 + 1 < static_cast<int>(gridDim.x) && sk_units * (sk_g1 + 1) / static_cast<long>(gridDim.x) < tile_end) ++sk_g1;
-        __threadfence();  // this thread's partial sums are visible device-wide before the arrival below
-        asm volatile("bar.sync 2, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
-        if (et == 0) {
-          int old;
-          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.sk_flags + item), "r"(1) : "memory");
-          *sk_last = old == sk_g1 - sk_g0;  // parts - 1 arrivals before this one: every other part is in the workspace
-          if (*sk_last) p.sk_flags[item] = 0;  // ready for the next launch (nobody else touches this tile any more)
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
-        if (!*sk_last) {
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-          asm volatile("bar.sync 2, %0;" ::"n"(kConvEpiWarps * 32) : "memory");  // sk_last is rewritten by the next partial segment
-          continue;
-        }
-        __threadfence();
-      }
 #pragma unroll 1
       for (int rd = 0; rd <= last_rd; ++rd) {
         const int c0 = rd * 64 + cg * 16;
         const int cbase = n0 + c0;
         const int ncols = min(16, limit - c0);  // 8 or 16
         uint32_t v[16];
-        if (!partial) {
-          tmem_ld_32x16(t_acc + c0, v);
-        } else {  // last arriver of a stream-K tile: the accumulator is the sum of the tile's workspace slots, in CTA order
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
-#pragma unroll 1
-          for (int g = sk_g0; g <= sk_g1; ++g) {
-            const int first_tile = static_cast<int>((sk_units * g / static_cast<long>(gridDim.x)) / kiters);
-            const float* ps = p.sk_ws + ((static_cast<size_t>(g) * 2 + (item == first_tile ? 0 : 1)) * kBlockM + row) * BLOCK_N + c0;
-            uint32_t pv[16];
-            asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(pv[0]), "=r"(pv[1]), "=r"(pv[2]), "=r"(pv[3]), "=r"(pv[4]), "=r"(pv[5]), "=r"(pv[6]), "=r"(pv[7]) : "l"(ps) : "memory");
-            asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(pv[8]), "=r"(pv[9]), "=r"(pv[10]), "=r"(pv[11]), "=r"(pv[12]), "=r"(pv[13]), "=r"(pv[14]), "=r"(pv[15]) : "l"(ps + 8) : "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(pv[j]));
-          }
-        }
+        tmem_ld_32x16(t_acc + c0, v);
         float4 bb[4];
         if (p.bias) {  // in flight together with the TMEM load
 #pragma unroll
@@ -446,15 +345,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
         }
-        if (!partial) {
-          tmem_ld_wait();
-          if (rd == last_rd) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
-              else mbar_arrive(&tmem_empty[acc]);
-            }
+        tmem_ld_wait();
+        if (rd == last_rd) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CLUSTER > 1 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
           }
         }
         f32x2 h[8];
@@ -544,7 +441,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
-      if (last_rd < 0 && !partial) {  // narrow or edge tile: nothing to read for this warp, still release the accumulator
+      if (last_rd < 0) {  // narrow or edge tile: nothing to read for this warp, still release the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -556,6 +453,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         // every epilogue warp has added its partial sums of this tile: one global atomic per group, then the slots are
         // cleared for the tile after next (the next tile uses the other parity, so no second barrier is needed)
         asm volatile("bar.sync 1, %0;" ::"n"(kConvEpiWarps * 32) : "memory");
+        const int et = static_cast<int>(threadIdx.x) - 64;  // 0 .. 511 over the epilogue warps
         const int ng = (limit + p.gn_gs - 1) / p.gn_gs;
         if (et < 2 * ng) {
           unsigned long long* slot = gn_acc + gpar * (kGnMaxLocal * 2) + et;
@@ -569,7 +467,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
         gpar ^= 1;
       }
-      if (partial) asm volatile("bar.sync 2, %0;" ::"n"(kConvEpiWarps * 32) : "memory");  // sk_last is rewritten by the next partial segment
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -587,7 +484,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 // ------------------------------------------------------------------------------------------- host side
 
 template <int BLOCK_N, int STAGES, int CLUSTER>
-static int launch_conv(ConvKernelParams& p, cudaStream_t stream, size_t p_sk_bytes = 0) {
+static int launch_conv(ConvKernelParams& p, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + (BLOCK_N / CLUSTER) * kBlockK * 2) + 1024 + 256 + kGnSmemBytes;
   static PerDeviceInt per_sm_dev;
   int& per_sm = per_sm_dev.get();
@@ -604,13 +501,6 @@ static int launch_conv(ConvKernelParams& p, cudaStream_t stream, size_t p_sk_byt
   const int items = p.n_tiles * ((p.m_tiles + CLUSTER - 1) / CLUSTER);
   int grid = std::min(items * CLUSTER, num_sms() * per_sm);
   grid -= grid % CLUSTER;
-  if (CLUSTER == 1 && p.sk_ws) {  // stream-K: equal unit ranges over one CTA per SM (every CTA owns at least one (tile, K-iteration) unit)
-    const long units = static_cast<long>(items) * p.ntaps * p.kchunks;
-    grid = static_cast<int>(std::min<long>(units, num_sms()));
-    const size_t need = static_cast<size_t>(2) * grid * kBlockM * BLOCK_N * sizeof(float) + static_cast<size_t>(items) * sizeof(int);
-    if (need > p_sk_bytes) return set_error(UC_EINVAL, "conv_gemm stream-K: workspace of %zu bytes needed, %zu given", need, p_sk_bytes);
-    p.sk_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(p.sk_ws) + p_sk_bytes) - items;  // counters at the end (zero between launches)
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads);
@@ -742,12 +632,8 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
 
   const int gn_gs = d->gn_stats ? d->Cout / d->gn_groups : 0;
   // block_n >= 1000 selects the cta_group::2 pair variant (1128 / 1192 / 1256)
-  // block_n >= 2000 selects stream-K scheduling of the single-CTA kernel (2064 ... 2256; needs sk_workspace)
-  const bool streamk = d->block_n >= 2000;
-  const bool cluster2 = !streamk && d->block_n >= 1000;
-  const int bn = streamk ? d->block_n - 2000 : cluster2 ? d->block_n - 1000 : d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
-  if (streamk && (!d->sk_workspace || (reinterpret_cast<uintptr_t>(d->sk_workspace) & 31) || d->sk_workspace_bytes % 4))
-    return set_error(UC_EINVAL, "uc_conv2d: stream-K (block_n >= 2000) needs a 32-byte aligned sk_workspace");
+  const bool cluster2 = d->block_n >= 1000;
+  const int bn = cluster2 ? d->block_n - 1000 : d->block_n ? d->block_n : pick_block_n(d->Cout, m_tiles, gn_gs);
   if (bn == 0) return set_error(UC_EINVAL, "uc_conv2d: no N tile compatible with GroupNorm group size %d", gn_gs);
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(nt), static_cast<uint64_t>(d->Cout)};
@@ -793,16 +679,14 @@ extern "C" int uc_conv2d(const UcConv2d* d, void* stream_v) {
       default: return set_error(UC_EINVAL, "uc_conv2d: the cta_group::2 variant exists for block_n 128/192/256 only");
     }
   }
-  const size_t skb = streamk ? static_cast<size_t>(d->sk_workspace_bytes) : 0;
-  p.sk_ws = streamk ? static_cast<float*>(d->sk_workspace) : nullptr;
   switch (bn) {
-    case 256: return launch_conv<256, 4, 1>(p, stream, skb);
-    case 192: return launch_conv<192, 5, 1>(p, stream, skb);
-    case 128: return launch_conv<128, 6, 1>(p, stream, skb);
-    case 96: return launch_conv<96, 6, 1>(p, stream, skb);
-    case 64: return launch_conv<64, 8, 1>(p, stream, skb);
-    case 32: return launch_conv<32, 8, 1>(p, stream, skb);
-    case 16: return launch_conv<16, 8, 1>(p, stream, skb);
+    case 256: return launch_conv<256, 4, 1>(p, stream);
+    case 192: return launch_conv<192, 5, 1>(p, stream);
+    case 128: return launch_conv<128, 6, 1>(p, stream);
+    case 96: return launch_conv<96, 6, 1>(p, stream);
+    case 64: return launch_conv<64, 8, 1>(p, stream);
+    case 32: return launch_conv<32, 8, 1>(p, stream);
+    case 16: return launch_conv<16, 8, 1>(p, stream);
     default: return set_error(UC_EINVAL, "uc_conv2d: unsupported block_n %d", bn);
   }
 }

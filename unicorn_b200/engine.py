@@ -185,23 +185,12 @@ class UnicornEngine:
                 bn = self._tune(x, w, k, stride, pad, out, kw, Cout, gn)
                 self._bn_dirty = True
             self._bn_cache[key] = bn
-        if bn >= 2000:
-            kw["sk_ws"] = self._sk_workspace()
         return ops.conv2d(x, w, k, k, stride, pad, out=out, block_n=bn, **kw)
-
-    def _sk_workspace(self):
-        """Stream-K reduction workspace of the CURRENT stream (kernels of different streams run concurrently — head levels, the
-        correlation chain next to the neck — and must not share one): 2 x 148 partial 128 x 256 fp32 tiles + tile counters, zeroed once
-        (the kernel leaves the counters zero)."""
-        return self.buf("conv.sk.%x" % torch.cuda.current_stream().cuda_stream, (2 * 148 * 128 * 256 + 16384,), F32, zero=True)
 
     def _tune(self, x, w, k, stride, pad, out, kw, Cout, gn):
         gs = Cout // gn if gn else 0
         cands = [0] + [b for b in (64, 96, 128, 192, 256) if (not gs or b % gs == 0) and b < 2 * Cout + 64]
         cands += [1000 + b for b in (128, 192, 256) if b in cands]  # 2-CTA cluster variants with weight multicast
-        m_tiles = -(-(x.shape[0] * out.shape[1] * out.shape[2]) // 128)
-        if os.environ.get("UC_STREAMK", "1") != "0":  # stream-K scheduling where whole tiles would leave SMs idle (few waves)
-            cands += [2000 + b for b in (64, 96, 128, 192, 256) if b in cands and m_tiles * -(-Cout // b) < 3 * 148]
         scratch = torch.empty_like(out)
         kw2 = dict(kw)
         if gn:
@@ -209,10 +198,6 @@ class UnicornEngine:
         best, best_t, times = 0, None, []
         reps = 6
         for bn in cands:
-            if bn >= 2000:
-                kw2["sk_ws"] = self._sk_workspace()
-            else:
-                kw2.pop("sk_ws", None)
             # timed as the frame runs it: back-to-back kernel nodes of a CUDA graph (stream launches of ~20 us kernels
             # measure launch cadence, not the kernel)
             try:
@@ -248,8 +233,6 @@ class UnicornEngine:
         fills in whatever is missing).  Returns the number of entries loaded."""
         import glob
         import json
-        if path is None and os.environ.get("UC_NO_TUNED"):
-            return 0  # plan-time autotuning of every layer (tools: regenerate the committed tables)
         if path is None:
             # keys are layer shapes, not config names: the tables of the other configs cover the layers they share with this
             # one (e.g. *_mask and *_mot_challenge differ from unicorn_track_large only in the head outputs); this config's

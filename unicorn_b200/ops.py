@@ -45,7 +45,7 @@ CONV_TRACE = None
 
 
 def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=None, res=None, out=None,
-           out_dtype=None, block_n=0, gn_stats=None, gn_groups=0, row_stats=None, col_s=None, row_eps=1e-6, sk_ws=None):
+           out_dtype=None, block_n=0, gn_stats=None, gn_groups=0, row_stats=None, col_s=None, row_eps=1e-6):
     """x: NHWC view (B,H,W,Cin) bf16/f16.  w_packed: [Cout, KH*KW, Cin].  Returns NHWC (B,Ho,Wo,Cout)."""
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
@@ -73,7 +73,6 @@ def conv2d(x, w_packed, KH, KW, stride=1, pad=0, bias=None, act=ACT_NONE, gamma=
     d.block_n = block_n
     d.gn_stats, d.gn_groups = _p(gn_stats), gn_groups
     d.row_stats, d.col_s, d.row_eps = _p(row_stats), _p(col_s), row_eps
-    d.sk_workspace, d.sk_workspace_bytes = (_p(sk_ws), sk_ws.numel() * sk_ws.element_size()) if sk_ws is not None else (None, 0)
     if row_stats is not None:
         assert row_stats.dtype == torch.int64 and row_stats.numel() == B * H * W * 2 and col_s is not None and col_s.numel() >= Cout
     if CONV_TRACE is not None:  # tools/profile_frame.py: conv launches in issue order, to label an ncu launch list
