@@ -67,8 +67,10 @@ def test_mot_mode_head_and_detections_vs_reference_golden(golden):
     head, seq = model(imgs=img, mode="whole")
     assert rel(seq["feat"][0, ::4], g["feat_sub"]) < 4e-2
     check_head(head, g["head"])
-    dets = postprocess(head, 8, float(g["conf"]), float(g["nms"]))[0]
-    assert dets is not None
+    head_cxcywh = head.clone()
+    dets = postprocess(head, 8, float(g["conf"]), float(g["nms"]))[0]  # like the reference's, it turns head's boxes into corners in place
+    assert dets is not None and torch.allclose(head[0, :, 2] - head[0, :, 0], head_cxcywh[0, :, 2], atol=1e-3)
+    head = head_cxcywh
     check_dets(dets.cpu(), g["dets"], orc)
     # the MOT driver's device half gives the same head output, bit for bit (same kernels, other buffers)
     from unicorn_b200.mot import UnicornMOTTracker

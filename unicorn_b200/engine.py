@@ -233,6 +233,8 @@ class UnicornEngine:
         fills in whatever is missing).  Returns the number of entries loaded."""
         import glob
         import json
+        if path is None and os.environ.get("UC_NO_TUNED"):
+            return 0  # plan-time autotuning of every layer (tools: regenerate the committed tables)
         if path is None:
             # keys are layer shapes, not config names: the tables of the other configs cover the layers they share with this
             # one (e.g. *_mask and *_mot_challenge differ from unicorn_track_large only in the head outputs); this config's
