@@ -148,7 +148,7 @@ def cpu_baseline_sample(cfg, H, W, budget_s=25.0):
             "sample": f"{n} full {H}x{W} SOT frame(s) after 1 warm-up frame, oracle (torch CPU fp32), {cores} threads"}
 
 
-def extra_workloads(dev, rank, world, K, sync_all):
+def extra_workloads(dev, rank, world, K, sync_all, save_tuning=None):
     """BASELINE configs[2] (ConvNeXt-L MOT at 1536x2048, ByteTrack association of 100 synthetic objects per frame) and configs[3]
     (ConvNeXt-L + CondInst mask head VOS at 800x1280, 1 and 3 objects) through the product drivers.  Per workload: `_dt_dev` =
     seconds for K CUDA-graph replays with the frames resident in HBM (CUDA events), `_dt_e2e` = wall clock of K frames through the
@@ -207,6 +207,8 @@ def extra_workloads(dev, rank, world, K, sync_all):
         mot_step(i)  # frames 1-2 eager (autotuning), 3-4 capture the two parity graphs
     dt_dev, dt_e2e = timed(mot_replay, mot_step, K)
     trk.collect()
+    if save_tuning:
+        eng.save_tuning(os.path.join(save_tuning, f"{cfg}.json"))
     out["mot_1536x2048"] = dict(_frames=K, _dt_dev=dt_dev, _dt_e2e=dt_e2e, gflop_per_frame=1887.7 * 3.072,
                                 workload=f"{cfg} MOT detector (mode whole, 64512 anchors) + ByteTrack association of 100 synthetic objects per frame, "
                                          "1536x2048 (BASELINE configs[2]); device half = CUDA graph, association of frame t overlapped with frame t+1",
@@ -238,6 +240,8 @@ def extra_workloads(dev, rank, world, K, sync_all):
                                                 h2d_bytes_per_step=int(host[0].numel()), d2h_bytes_per_step=int(n_obj * 32),
                                                 launches_per_frame=vos.launches_per_frame)
         del vos
+    if save_tuning:
+        eng.save_tuning(os.path.join(save_tuning, f"{cfg}.json"))
     return out
 
 
@@ -255,6 +259,7 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] (MOT 1536x2048) and configs[3] (VOS mask) workloads")
+    ap.add_argument("--save-tuning", default=None, help="directory: write every engine's per-layer N-tile table (with UC_NO_TUNED=1: fresh autotuning)")
     args = ap.parse_args()
     if args.size is None:
         args.size = (320, 320) if "tiny" in args.config else (800, 1280)
@@ -412,7 +417,9 @@ def main():
                                "M = 4000 pixels, CUDA-graph nodes",
                      "peak_source": "measured bf16_tflops (burst)"}
 
-    extra = {} if args.no_extra else extra_workloads(dev, rank, world, max(8, min(K, 24)), sync_all)
+    extra = {} if args.no_extra else extra_workloads(dev, rank, world, max(8, min(K, 24)), sync_all, args.save_tuning if rank == 0 else None)
+    if args.save_tuning and rank == 0:
+        eng.save_tuning(os.path.join(args.save_tuning, f"{args.config}.json"))
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e, dt_dev_pipe, dt_e2e_pipe] + [v for k in sorted(extra) for v in (extra[k]["_dt_dev"], extra[k]["_dt_e2e"])], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -28,7 +28,10 @@ def timed(fn):
     return a.elapsed_time(b) * 1e3 / (2 * R)
 
 
+ONLY = [a for a in sys.argv[1:]]
 for name, H, W, C in SHAPES:
+    if ONLY and name not in ONLY:
+        continue
     x = torch.randn(1, H, W, C, device=dev).bfloat16()
     w = ops.pack_dw_weight(torch.randn(C, 1, 7, 7, device=dev) / 7)
     b, lw, lb = (torch.randn(C, device=dev) for _ in range(3))
