@@ -311,17 +311,31 @@ class UnicornEngine:
         # two launches: the channel-chunked tiled depthwise kernel + a row LayerNorm on the L2-resident result.  The fused
         # one-CTA-per-pixel-tile kernel (ops.dwconv7_ln) was measured slower on every stage of ConvNeXt-L (34.6 vs 28 us on
         # stage 3: 2.3x the instructions per output, 8 warps per SM) — see DESIGN.md 4.3.
+        # The 4C hidden map of the first stages is larger than what stays in L2 next to everything else (64000 x 768 x 2 B = 98 MB in
+        # stage 1): pwconv1 -> pwconv2 then pays an HBM round trip for it.  Run the pair per band of rows instead, with ONE band-sized
+        # hidden buffer that is rewritten by every band and therefore never leaves L2 (UC_MLP_BAND_MB = its size limit, 0 = off).
+        band_mb = float(os.environ.get("UC_MLP_BAND_MB", "32"))
+        nb = 1
+        if band_mb > 0 and B == 1:
+            nb = max(1, -(-(H * W * 4 * C * 2) // int(band_mb * 2 ** 20)))
+            while H % nb:
+                nb += 1
+        hb = H // nb
+        hid = self.buf(tag + ".h", (B, hb, W, 4 * C))
         if self.ln_fold and C % 32 == 0:
             rs = self._row_stats(B * H * W)
             t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), ln_stats=rs, work_counter=self._ctr())
-            hid = self.conv(t, bp["w1f"], 1, bias=bp["c1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)),
-                            row_stats=rs, col_s=bp["s1"], row_eps=1e-6)
-            self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
+            for i in range(nb):
+                xs, ts = x[:, i * hb:(i + 1) * hb], t[:, i * hb:(i + 1) * hb]
+                self.conv(ts, bp["w1f"], 1, bias=bp["c1"], act=ACT_GELU, out=hid, row_stats=rs[i * hb * W:(i + 1) * hb * W], col_s=bp["s1"], row_eps=1e-6)
+                self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=xs, out=xs)
             return x
         t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
-        hid = self.conv(t, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=self.buf(tag + ".h", (B, H, W, 4 * C)))
-        self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=x, out=x)
+        for i in range(nb):
+            xs, ts = x[:, i * hb:(i + 1) * hb], t[:, i * hb:(i + 1) * hb]
+            self.conv(ts, bp["w1"], 1, bias=bp["b1"], act=ACT_GELU, out=hid)
+            self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=xs, out=xs)
         return x
 
     def csp(self, x, cp, out, tag):
