@@ -86,7 +86,6 @@ def test_qd_assign_kernel_matches_reference_loop():
                     ref[i] = -2
         got = ops.qd_assign(sc.cuda().contiguous(), memo_ids.cuda(), boxes.cuda().contiguous(), 0.5, 0.5, 0.6).cpu()
         assert torch.equal(got, ref), (N, M)
-    assert trk.num_tracklets == int(g["num_tracklets"])
 
 
 def test_mot_driver_runs_and_is_consistent():
