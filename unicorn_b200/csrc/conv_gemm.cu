@@ -49,8 +49,8 @@ struct alignas(64) ConvKernelParams {
   int ldres;
   void* y;
   int ldy, y_dtype, act;
-  int wide_store, wide_res;
-  int debug;  // tools only (UC_CONV_DEBUG): 1 = no MMA (operand feed rate alone), 2 = no TMA loads (MMA + epilogue alone)  // 256-bit stores / residual loads possible (32-byte aligned rows)
+  int wide_store, wide_res;  // 256-bit stores / residual loads possible (32-byte aligned rows)
+  int debug;  // tools only (UC_CONV_DEBUG): 1 = no MMA (operand feed rate alone), 2 = no TMA loads (MMA + epilogue alone)
   const long long* row_stats;  // LayerNorm folded into this 1x1 conv: per input pixel {sum, sumsq} (fixed point 2^22) ...
   const float* col_s;          // ... column sums of the folded weights, channel count and epsilon of the LayerNorm
   float row_inv, row_eps;  // row_inv = 1 / (2^22 * Cin)
@@ -79,7 +79,7 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 // max |error| 3.3e-6 over the whole real line (tools/fit_gelu.py; the bf16 output ulp is >= 1.5e-5 wherever |y| > 4e-3,
 // and the fit saturates correctly: y -> x for x -> +inf, y -> -0 for x -> -inf).  Per PAIR of elements: 8 packed
 // FMA-pipe instructions + 2 x (ex2, rcp) — the earlier Abramowitz-Stegun form cost ~25 issue slots per element and the
-// epilogue, not the tensor pipe, set the pace of every pwconv1 (ncu: profiles/r1_ncu_conv_epilogue.md).
+// epilogue, not the tensor pipe, set the pace of every pwconv1 (round-1 ncu source view; DESIGN.md 4.1 history).
 __device__ __forceinline__ f32x2 gelu2(f32x2 x) {
   // coefficients pre-multiplied by -log2(e): e = 2^(x * P'(x^2)) = exp(-q(x))
   const f32x2 c0 = pk2(-2.30204844f, -2.30204844f), c1 = pk2(-0.105217814f, -0.105217814f), c2 = pk2(3.54831049e-4f, 3.54831049e-4f),
