@@ -312,9 +312,11 @@ class UnicornEngine:
         # one-CTA-per-pixel-tile kernel (ops.dwconv7_ln) was measured slower on every stage of ConvNeXt-L (34.6 vs 28 us on
         # stage 3: 2.3x the instructions per output, 8 warps per SM) — see DESIGN.md 4.3.
         # The 4C hidden map of the first stages is larger than what stays in L2 next to everything else (64000 x 768 x 2 B = 98 MB in
-        # stage 1): pwconv1 -> pwconv2 then pays an HBM round trip for it.  Run the pair per band of rows instead, with ONE band-sized
-        # hidden buffer that is rewritten by every band and therefore never leaves L2 (UC_MLP_BAND_MB = its size limit, 0 = off).
-        band_mb = float(os.environ.get("UC_MLP_BAND_MB", "32"))
+        # stage 1): pwconv1 -> pwconv2 pays an HBM round trip for it.  Running the pair per band of rows with ONE band-sized hidden
+        # buffer (rewritten by every band, so it never leaves L2) was MEASURED SLOWER — 243.8 vs 247.5 frames/s at 800x1280 and 89.7 vs
+        # 102.5 at 1536x2048 with 32 MB bands: four times the launches on a quarter of the rows cost more than the round trip saves
+        # (profiles/README.md) — so it is off by default (UC_MLP_BAND_MB = band size limit in MB enables it).
+        band_mb = float(os.environ.get("UC_MLP_BAND_MB", "0"))
         nb = 1
         if band_mb > 0 and B == 1:
             nb = max(1, -(-(H * W * 4 * C * 2) // int(band_mb * 2 ** 20)))
