@@ -245,6 +245,13 @@ def extra_workloads(dev, rank, world, K, sync_all, save_tuning=None):
     return out
 
 
+def roofline_inputs():
+    """Per-launch DRAM traffic of the kernels quoted below, from the committed ncu captures of the CURRENT kernels
+    (profiles/r2_roofline_inputs.json, written by tools/make_roofline_inputs.py from profiles/r2_ncu_*.csv)."""
+    path = os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")
+    return json.load(open(path)) if os.path.exists(path) else {"kernels": {}}
+
+
 def pk_burst():
     return peaks()["tf_burst"]
 
@@ -395,6 +402,7 @@ def main():
     # ---------------- dominant kernel: conv_gemm on the two stage-3 pointwise GEMM shapes (54 of the 172 conv launches of
     # a frame, 37 % of its device time), timed the way the frame runs them: kernel nodes of a CUDA graph, CUDA events.
     conv_roof = None
+    RI = roofline_inputs()
     if "large" in args.config and (H, W) == (800, 1280):
         xs = torch.randn(1, 50, 80, 768, device=dev).bfloat16()
         w1 = ops.pack_conv_weight(torch.randn(3072, 768, 1, 1, device=dev) / 768 ** 0.5)
@@ -424,8 +432,9 @@ def main():
         fl = 2 * 2.0 * 4000 * 768 * 3072
         conv_roof = {"bound": "tensor", "achieved": fl / t_pair / 1e12, "peak": pk_burst(), "unit": "TFLOP/s",
                      "frac": fl / t_pair / 1e12 / pk_burst(), "us_per_launch": t_pair * 1e6 / 2,
-                     "traffic": 35.5e6, "traffic_note": "ncu --set full, pwconv2 launch, cold L2: 35.5 MB DRAM = A 24.6 + W 4.7 + residual 6.1 "
-                                "(the algorithmic bytes); profiles/r1_ncu_prof_conv_s3pw2.csv",
+                     "traffic": RI["kernels"].get("r2_ncu_conv_s3pw2", {}).get("dram_bytes"),
+                     "traffic_note": "dram__bytes_read + write of the pwconv2 launch (conv_gemm_kernel<192,7,2>), ncu --set full, cold L2: A 24.6 + W 4.7 + residual "
+                                     "6.1 MB = the algorithmic bytes; profiles/r2_ncu_conv_gn.csv (pwconv1: r2_ncu_conv_s3pw1, 10.9 MB = A 6.1 + W 4.7)",
                      "kernel": "uc::conv_gemm_kernel, ConvNeXt-L stage-3 pwconv1 (768->3072, GELU) + pwconv2 (3072->768, layer-scale + residual), "
                                "M = 4000 pixels, CUDA-graph nodes",
                      "peak_source": "measured bf16_tflops (burst)"}
@@ -433,6 +442,7 @@ def main():
     extra = {} if args.no_extra else extra_workloads(dev, rank, world, max(8, min(K, 24)), sync_all, args.save_tuning if rank == 0 else None)
     if args.save_tuning and rank == 0:
         eng.save_tuning(os.path.join(args.save_tuning, f"{args.config}.json"))
+    RI_frame = RI.get("frame", {})
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e, dt_dev_pipe, dt_e2e_pipe, dt_dev_pipe3] + [v for k in sorted(extra) for v in (extra[k]["_dt_dev"], extra[k]["_dt_e2e"])], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -461,10 +471,14 @@ def main():
                                                                 "ms_per_step = timed region / steps; per-frame latency is the `sequential` entry's",
                    "input": "uint8 HWC BGR frames (3.07 MB H2D per frame); float conversion fused into the stem kernel"},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                     "traffic": None, "kernel": "whole-frame CUDA graph (1997 GFLOP algorithmic per 800x1280 frame, SURVEY §8d)",
+                     "traffic": RI_frame.get("dram_bytes"), "traffic_note": RI_frame.get("note"),
+                     "kernel": "whole-frame CUDA graph (1997 GFLOP algorithmic per 800x1280 frame, SURVEY §8d)",
                      "peak_source": pk["src"] + " bf16_tflops_sustained"},
         "roofline_conv": conv_roof,
-        "roofline_corr": {"bound": "tensor", "traffic": 8.28e6, "achieved": CORR_GFLOP(n_pos) / t_corr / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+        "roofline_corr": {"bound": "tensor", "traffic": RI["kernels"].get("r2_ncu_corr", {}).get("dram_bytes"),
+                          "hbm_note": "the fused kernel moves only its algorithmic 8.26 MB (the 16000^2 similarity matrix never leaves the SM), so it is bound "
+                                      "by the tensor / MUFU / issue pipes, not by HBM: hbm_frac is reported because BASELINE.json's metric asks for it, it is not a "
+                                      "utilisation target", "achieved": CORR_GFLOP(n_pos) / t_corr / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                           "frac": CORR_GFLOP(n_pos) / t_corr / 1e3 / pk["tf_burst"], "us_per_launch": t_corr * 1e6,
                           "hbm_gbs_algorithmic": CORR_BYTES(n_pos) / t_corr / 1e9, "hbm_frac": CORR_BYTES(n_pos) / t_corr / 1e9 / pk["hbm"],
                           "kernel": "uc::corr_kernel<1> (fused K^TQ + softmax + PV), L2 flushed between launches",
