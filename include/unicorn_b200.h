@@ -118,6 +118,12 @@ UC_API int uc_dwconv7_ln(const void* x_bf16, const float* w49, const float* bias
 UC_API int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, void* y_bf16, int B, int H, int W, int C,
                       void* ln_stats, int* work_counter, void* stream);
 
+/* The same depthwise 7x7 + bias on tensor cores (csrc/dwconv_mma.cu): every filter row is a banded 16 x 8 Toeplitz block applied with
+ * mma.sync.m16n8k16 to a channel-planar copy of the input tile.  qtab = per 32-channel chunk {int32 [32][7][8]: the filter as bf16
+ * tap pairs {f[kh][j-1], f[kh][j]}, j = 0..7, zero outside the row; fp32 [32]: the biases}, zero for the channels that pad C to a
+ * multiple of 32 (unicorn_b200.ops.pack_dw_weight_mma); C % 8 == 0.  Same x / y / work_counter conventions as uc_dwconv7; no ln_stats. */
+UC_API int uc_dwconv7_mma(const void* x_bf16, const void* qtab, void* y_bf16, int B, int H, int W, int C, int* work_counter, void* stream);
+
 /* Row LayerNorm: y[m,:] = LN(x[m,:] + res[m,:]) * w + b  (res may be NULL).  16-bit rows with element strides.
  * convnext.py:176-184 (downsample / out norms), deformable_transformer.py:113,121,127-130 (post-norm). */
 UC_API int uc_layernorm(const void* x, int ldx, const void* res, int ldres, const float* w, const float* b, void* y,

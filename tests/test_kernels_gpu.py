@@ -67,6 +67,15 @@ def test_dwconv_tiled(C, H, W):
     of = out.float().reshape(-1, C).double()
     assert torch.allclose(st[:, 0].double() / 4194304.0, of.sum(1), rtol=1e-5, atol=1e-3)
     assert torch.allclose(st[:, 1].double() / 4194304.0, (of ** 2).sum(1), rtol=1e-5, atol=1e-3)
+    # the tensor-core kernel (Toeplitz blocks on mma.sync; taps in bf16): against the same convolution with the taps it uses, and
+    # within bf16-tap rounding of the fp32-tap one; static and counter schedules give the same bits
+    wf = ops.pack_dw_weight_mma(w, b)
+    om = ops.dwconv7_mma(x, wf)
+    refb = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=3, groups=C).permute(0, 2, 3, 1)
+    close(om, refb, 5e-3, "dwconv mma (bf16 taps)")
+    close(om, ref, 8e-3, "dwconv mma vs fp32 taps")
+    om2 = ops.dwconv7_mma(x, wf, work_counter=torch.zeros(1, dtype=torch.int32, device=dev))
+    assert torch.equal(om, om2)
 
 
 @pytest.mark.parametrize("C", [96, 100, 192, 256, 384, 768, 1536, 2048])  # 100: not a multiple of 8 -> the 32-bit-access kernel

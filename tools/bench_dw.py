@@ -40,8 +40,10 @@ for name, H, W, C in SHAPES:
     t_dw = timed(lambda k: ops.dwconv7(x, w, b, out=y, work_counter=CTR[k:k + 1]))
     t_static = timed(lambda k: ops.dwconv7(x, w, b, out=y))
     t_st = timed(lambda k: ops.dwconv7(x, w, b, out=y, ln_stats=st, work_counter=CTR[k:k + 1]))
+    wf = ops.pack_dw_weight_mma(torch.randn(C, 1, 7, 7, device=dev) / 7, b)
+    t_mma = timed(lambda k: ops.dwconv7_mma(x, wf, out=y, work_counter=CTR[k:k + 1]))
     t_ln = timed(lambda k: ops.layernorm(y.view(-1, C), lw, lb, 1e-6, out=y.view(-1, C)))
     byt = 4.0 * H * W * C  # algorithmic bytes: read + write the bf16 map once
     fl = 98.0 * H * W * C
     print(f"{name:7s} {H:4d}x{W:<4d} C={C:5d}  dwconv {t_dw:7.1f} us ({byt/t_dw/1e3:7.1f} GB/s = {byt/t_dw/1e3/HBM*100:5.1f}% HBM, {fl/t_dw/1e6:5.1f} TFLOP/s fp32)"
-          f"  static-schedule {t_static:7.1f} us  +stats {t_st:7.1f} us  layernorm {t_ln:6.1f} us  tiled={os.environ.get('UC_DW_TILED', '0')}", flush=True)
+          f"  MMA {t_mma:7.1f} us ({byt/t_mma/1e3/HBM*100:5.1f}% HBM)  static-schedule {t_static:7.1f} us  +stats {t_st:7.1f} us  layernorm {t_ln:6.1f} us  tiled={os.environ.get('UC_DW_TILED', '0')}", flush=True)

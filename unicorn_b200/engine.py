@@ -55,6 +55,8 @@ class UnicornEngine:
         # ln_fold: the ConvNeXt blocks' LayerNorm is folded into pwconv1 (statistics from the depthwise kernel, normalisation in
         # the GEMM epilogue) — UNTESTED on a GPU (round-2 item); off unless asked for / UC_LN_FOLD=1
         self.ln_fold = bool(int(os.environ.get("UC_LN_FOLD", "0"))) if ln_fold is None else bool(ln_fold)
+        # depthwise 7x7 on tensor cores (csrc/dwconv_mma.cu; taps rounded to bf16) instead of the fp32-FMA kernel (csrc/dwconv_tma.cu)
+        self.dw_mma = bool(int(os.environ.get("UC_DW_MMA", "1")))
         self._row_arena, self._row_used = None, 0
         self._ctr_arena, self._ctr_used = None, 0  # work counters of the dynamically scheduled kernels (zeroed by begin_frame)
         self.autotune = autotune
@@ -89,7 +91,7 @@ class UnicornEngine:
             P[f"outnorm{i}"] = (f(b + f"norm{i}.weight"), f(b + f"norm{i}.bias"))
 
         def block(p):
-            d = dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
+            d = dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwm=ops.pack_dw_weight_mma(sd[p + "dwconv.weight"].to(dev), sd[p + "dwconv.bias"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
                      lnb=f(p + "norm.bias"), w1=pw(p + "pwconv1.weight"), b1=f(p + "pwconv1.bias"), w2=pw(p + "pwconv2.weight"),
                      b2=f(p + "pwconv2.bias"), gamma=f(p + "gamma"))
             if self.ln_fold:  # W' = W diag(g) (16-bit), colsum(W') of the ROUNDED weights, c = W beta + b
@@ -332,7 +334,10 @@ class UnicornEngine:
                 self.conv(ts, bp["w1f"], 1, bias=bp["c1"], act=ACT_GELU, out=hid, row_stats=rs[i * hb * W:(i + 1) * hb * W], col_s=bp["s1"], row_eps=1e-6)
                 self.conv(hid, bp["w2"], 1, bias=bp["b2"], gamma=bp["gamma"], res=xs, out=xs)
             return x
-        t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
+        if self.dw_mma and C % 8 == 0:
+            t = ops.dwconv7_mma(x, bp["dwm"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
+        else:
+            t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
         ops.layernorm(t.view(-1, C), bp["lnw"], bp["lnb"], 1e-6, out=t.view(-1, C))
         for i in range(nb):
             xs, ts = x[:, i * hb:(i + 1) * hb], t[:, i * hb:(i + 1) * hb]

@@ -121,6 +121,31 @@ def pack_dw_weight(w):
     return w.reshape(w.shape[0], 49).t().contiguous().float()
 
 
+def pack_dw_weight_mma(w, bias):
+    """[C,1,7,7], [C] -> int32 [ceil(C/32), 1824]: per 32-channel chunk the bf16 tap pairs {e[j-1], e[j]}, j = 0..7, of every channel
+    and filter row ([32][7][8] words; e = the row padded with zeros, lower index in the low half) followed by the 32 fp32 biases; zero
+    for the channels that pad C to a multiple of 32 — the operand of uc_dwconv7_mma, which builds the B fragments of its Toeplitz
+    blocks T[k][n] = e[k-n-1] from it."""
+    C = w.shape[0]
+    Cp = -(-C // 32) * 32
+    e = torch.zeros(Cp, 7, 9, dtype=torch.bfloat16, device=w.device)  # e[-1] .. e[7]
+    e[:C, :, 1:8] = w.reshape(C, 7, 7).to(torch.bfloat16)
+    bits = e.view(torch.int16).to(torch.int32) & 0xffff
+    pairs = (bits[:, :, 0:8] | (bits[:, :, 1:9] << 16)).to(torch.int32).reshape(Cp // 32, 32 * 7 * 8)
+    bp = torch.zeros(Cp, dtype=torch.float32, device=w.device)
+    bp[:C] = bias.float()
+    return torch.cat([pairs, bp.view(torch.int32).reshape(Cp // 32, 32)], dim=1).contiguous()
+
+
+def dwconv7_mma(x, qtab, out=None, work_counter=None):
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16 and qtab.dtype == torch.int32 and qtab.shape == (-(-C // 32), 1824)
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_L().uc_dwconv7_mma(_p(x), _p(qtab), _p(out), B, H, W, C, _p(work_counter), _S()), "uc_dwconv7_mma")
+    return out
+
+
 def stem_ln(img, w48, bias, lnw, lnb, eps=1e-6):
     """img: fp32 NCHW [B,3,H,W] or uint8 NHWC [B,H,W,3] (BGR)."""
     u8 = img.dtype == torch.uint8
