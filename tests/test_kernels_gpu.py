@@ -78,6 +78,36 @@ def test_dwconv_tiled(C, H, W):
     assert torch.equal(om, om2)
 
 
+@pytest.mark.parametrize("C,M", [(192, 128), (192, 1000), (96, 777), (192, 64000), (96, 40000)])
+def test_convnext_mlp_fused(C, M):
+    """uc_convnext_mlp (LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual in one launch, convnext.py:45-52) against
+    the same chain in fp32 torch on the bf16 inputs / weights, and against the unfused kernels of the library."""
+    from unicorn_b200 import ops
+    g = G(5)
+    t = (torch.randn(M, C, generator=g) * 1.5 + 0.3).to(dev).bfloat16()
+    x = torch.randn(M, C, generator=g).to(dev).bfloat16()
+    lw, lb = (1 + 0.2 * torch.randn(C, generator=g)).to(dev), (0.1 * torch.randn(C, generator=g)).to(dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dev)
+    b1 = (0.1 * torch.randn(4 * C, generator=g)).to(dev)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dev)
+    b2 = (0.1 * torch.randn(C, generator=g)).to(dev)
+    gamma = (0.5 * torch.randn(C, generator=g)).to(dev)
+    w1f = (w1 * lw[None, :]).bfloat16().contiguous()
+    c1 = (w1 @ lb + b1).contiguous()
+    w2b = w2.bfloat16().contiguous()
+    out = ops.convnext_mlp(t, w1f, c1, w2b, b2, gamma, x.clone())
+    tn = F.layer_norm(t.float(), (C,), None, None, 1e-6).bfloat16().float()
+    hid = F.gelu(tn @ w1f.float().t() + c1).bfloat16().float()
+    ref = x.float() + gamma * (hid @ w2b.float().t() + b2)
+    close(out, ref, 6e-3, "fused convnext mlp")
+    # rows past M in the last tile are not written; the call is deterministic
+    assert torch.equal(out, ops.convnext_mlp(t, w1f, c1, w2b, b2, gamma, x.clone()))
+    # the unfused library path (uc_layernorm with affine, two uc_conv2d): same result within bf16 rounding of the intermediate maps
+    tl = ops.layernorm(t, lw, lb, 1e-6)
+    ref2 = x.float() + gamma * (F.gelu(tl.float() @ w1.bfloat16().float().t() + b1).bfloat16().float() @ w2b.float().t() + b2)
+    close(out, ref2, 2e-2, "fused vs unfused formulation")
+
+
 @pytest.mark.parametrize("C", [96, 100, 192, 256, 384, 768, 1536, 2048])  # 100: not a multiple of 8 -> the 32-bit-access kernel
 def test_layernorm(C):
     from unicorn_b200 import ops

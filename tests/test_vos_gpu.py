@@ -64,6 +64,7 @@ def _run_driver(use_graph, keep_soft=False):
     name, size, new_at = str(g["config"]), tuple(int(v) for v in g["size"]), int(g["new_at"])
     rgb, xywh, lab = make_sequence()
     trk = UnicornVOSTrack(UnicornEngine(make_state_dict(name, 0), name), size, use_graph=use_graph)
+    trk.debug = keep_soft  # keep a copy of every object's head output (the score margins of the parity test)
     trk.initialize(rgb[0], {"init_object_ids": ["1", "2"], "sequence_object_ids": ["1", "2", "3"],
                             "init_bbox": {"1": xywh[0, 0].tolist(), "2": xywh[0, 1].tolist()}})
     segs, states, softs = [], [], []
@@ -73,7 +74,8 @@ def _run_driver(use_graph, keep_soft=False):
         segs.append(trk.track(rgb[t], info)["segmentation"].copy())
         states.append([trk.state_pre_dict[o] for o in ("1", "2")])
         if keep_soft:
-            softs.append(trk._soft[:n_obj].cpu().numpy().copy())
+            heads = {o: po["head"].float().cpu() for o, po in trk.last["per_obj"].items()}
+            softs.append((trk._soft[:n_obj].cpu().numpy().copy(), heads))
     return g, segs, states, softs
 
 
@@ -93,38 +95,80 @@ def _oracle_softs(g):
         new = {"3": box_xyxy(xywh[t, 2], r)} if t == new_at else None
         seg, res = o.track(prep_frame(rgb[t], size), new, lab if t == new_at else None)
         ids = ["1", "2"] + (["3"] if t >= new_at else [])
-        out.append((seg, np.stack([np.asarray(res[i]["soft"], dtype=np.float32) for i in ids])))
+        out.append((seg, np.stack([np.asarray(res[i]["soft"], dtype=np.float32) for i in ids]),
+                    {i: res[i]["head"] for i in ids if res[i].get("head") is not None}))
     return out
+
+
+def _top1_margin(head):
+    """head [1,N,6] (cx, cy, w, h, obj, cls): (corner box of the best-scoring anchor, its score lead over the best anchor that
+    is a DIFFERENT instance (IoU < 0.5 with it), all scores)."""
+    import unicorn_oracle as orc
+    h = head[0].float()
+    sc = h[:, 4] * h[:, 5]
+    b = torch.stack([h[:, 0] - h[:, 2] / 2, h[:, 1] - h[:, 3] / 2, h[:, 0] + h[:, 2] / 2, h[:, 1] + h[:, 3] / 2], 1)
+    k = int(sc.argmax())
+    iou = torch.from_numpy(orc.box_iou_np(b[k:k + 1].numpy(), b.numpy())[0])
+    other = sc[iou < 0.5]
+    return b[k], float(sc[k] - (other.max() if other.numel() else 0.0)), sc
 
 
 def test_vos_driver_vs_reference_class_golden():
     """Label maps of the product driver (reference protocol: RGB frames in, `segmentation` out) against the UNMODIFIED reference
-    class's.  A pixel's label is an argmax over soft masks; with seeded random weights those are noise-like, so the comparison is
-    margin aware: where the fp32 oracle's winning channel leads by more than MARGIN the engine must agree (>= 99 %), the raw
-    agreement is reported and loosely bounded, and the engine's soft masks must stay within SOFT_TOL of the oracle's."""
+    class's.  Two decisions feed a pixel's label, and with seeded random weights both are near ties, so both are compared margin aware:
+      * per object, WHICH instance gets the mask (top-1 of obj * cls after NMS, unicorn_vos.py:137-155).  It is well conditioned when
+        the fp32 oracle's best anchor leads every different instance by more than twice the largest score error of the engine on that
+        object: then the engine must pick the same instance, and wherever both picked the same instance (conditioned or not) its soft
+        mask must stay within SOFT_TOL of the oracle's.  Picks of another instance on an ill-conditioned object are counted and reported;
+      * per pixel, the argmax over the soft masks: where the oracle's winning channel leads by more than MARGIN the engine must agree
+        (>= 99 %); the raw agreement is reported and bounded on the frames without an instance flip."""
+    import unicorn_oracle as orc
     MARGIN, SOFT_TOL = 0.12, 0.12  # measured soft-mask drift p99 <= 0.036: the margin is > 3x that
     g, segs, states, softs = _run_driver(False, keep_soft=True)
     orc_frames = _oracle_softs(g)
-    report = dict(raw_agreement=[], conditioned_agreement=[], conditioned_fraction=[], soft_err_p99=[], oracle_vs_reference=[])
+    new_at = int(g["new_at"])
+    report = dict(raw_agreement=[], conditioned_agreement=[], conditioned_fraction=[], soft_err_p99=[], oracle_vs_reference=[],
+                  instance_flips=[], well_conditioned_objects=0, objects=0)
     for t, (s, r) in enumerate(zip(segs, g["segs"])):
-        o_seg, o_soft = orc_frames[t]
+        o_seg, o_soft, o_heads = orc_frames[t]
+        e_soft, e_heads = softs[t]
+        ids = ["1", "2"] + (["3"] if t + 1 >= new_at else [])
+        same = []
+        for k, oid in enumerate(ids):
+            if oid not in o_heads or oid not in e_heads:  # the frame where the object appears: its mask is the given label map
+                same.append(k)
+                continue
+            ob, margin, osc = _top1_margin(o_heads[oid])
+            eb, _, esc = _top1_margin(e_heads[oid])
+            eps = float((osc - esc).abs().max())
+            agree = orc.box_iou_np(ob[None].numpy(), eb[None].numpy())[0, 0] > 0.5
+            report["objects"] += 1
+            if margin > 2 * eps:
+                report["well_conditioned_objects"] += 1
+                assert agree, (t, oid, margin, eps)
+            if agree:
+                same.append(k)
+            else:
+                report["instance_flips"].append((t, oid, margin, eps))
         chans = np.concatenate([np.prod(1 - o_soft, axis=0, keepdims=True), o_soft], 0)
         top2 = np.sort(chans, axis=0)[-2:]
         cond = (top2[1] - top2[0]) > MARGIN
-        report["raw_agreement"].append(float((s == r).mean()))
-        report["conditioned_agreement"].append(float((s == r)[cond].mean()) if cond.any() else 1.0)
+        if len(same) == len(ids):
+            report["raw_agreement"].append(float((s == r).mean()))
+            report["conditioned_agreement"].append(float((s == r)[cond].mean()) if cond.any() else 1.0)
         report["conditioned_fraction"].append(float(cond.mean()))
         report["oracle_vs_reference"].append(float((o_seg == r).mean()))
-        report["soft_err_p99"].append(float(np.percentile(np.abs(softs[t] - o_soft), 99)))
+        report["soft_err_p99"].append(float(np.percentile(np.abs(e_soft[same] - o_soft[same]), 99)) if same else 0.0)
     print("VOS driver vs the reference class:", report)
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
         import json
         json.dump(report, open(os.path.join(out, "r2_vos_parity.json"), "w"), indent=1)
+    assert len(report["instance_flips"]) <= 2 and len(report["raw_agreement"]) >= 2, report
     assert min(report["conditioned_agreement"]) > 0.99, report
     assert min(report["raw_agreement"]) > 0.8, report
     assert max(report["soft_err_p99"]) < SOFT_TOL, report
-    assert segs[int(g["new_at"]) - 1].max() == 3  # the new object's initial mask went through the aggregation
+    assert segs[new_at - 1].max() == 3  # the new object's initial mask went through the aggregation
     print("max |state box - reference| (pixels):", np.abs(np.array(states, dtype=np.float32) - g["states"]).max())
 
 

@@ -57,6 +57,8 @@ class UnicornEngine:
         self.ln_fold = bool(int(os.environ.get("UC_LN_FOLD", "0"))) if ln_fold is None else bool(ln_fold)
         # depthwise 7x7 on tensor cores (csrc/dwconv_mma.cu; taps rounded to bf16) instead of the fp32-FMA kernel (csrc/dwconv_tma.cu)
         self.dw_mma = bool(int(os.environ.get("UC_DW_MMA", "1")))
+        # LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual of the blocks with C = 96 / 192 in one launch (csrc/mlp_fused.cu)
+        self.mlp_fused = bool(int(os.environ.get("UC_MLP_FUSED", "1")))
         self._row_arena, self._row_used = None, 0
         self._ctr_arena, self._ctr_used = None, 0  # work counters of the dynamically scheduled kernels (zeroed by begin_frame)
         self.autotune = autotune
@@ -94,7 +96,8 @@ class UnicornEngine:
             d = dict(dw=ops.pack_dw_weight(sd[p + "dwconv.weight"].to(dev)), dwm=ops.pack_dw_weight_mma(sd[p + "dwconv.weight"].to(dev), sd[p + "dwconv.bias"].to(dev)), dwb=f(p + "dwconv.bias"), lnw=f(p + "norm.weight"),
                      lnb=f(p + "norm.bias"), w1=pw(p + "pwconv1.weight"), b1=f(p + "pwconv1.bias"), w2=pw(p + "pwconv2.weight"),
                      b2=f(p + "pwconv2.bias"), gamma=f(p + "gamma"))
-            if self.ln_fold:  # W' = W diag(g) (16-bit), colsum(W') of the ROUNDED weights, c = W beta + b
+            d["fused"] = self.mlp_fused and ops.convnext_mlp_supported(d["lnw"].numel())
+            if self.ln_fold or d["fused"]:  # W' = W diag(g) (16-bit), colsum(W') of the ROUNDED weights, c = W beta + b
                 w1 = sd[p + "pwconv1.weight"].to(dev, F32).reshape(d["b1"].numel(), -1)
                 d["w1f"] = ops.pack_conv_weight((w1 * d["lnw"][None, :])[:, :, None, None])
                 d["s1"] = d["w1f"].float().sum(dim=(1, 2)).contiguous()
@@ -325,6 +328,13 @@ class UnicornEngine:
             while H % nb:
                 nb += 1
         hb = H // nb
+        if bp.get("fused"):
+            if self.dw_mma:
+                t = ops.dwconv7_mma(x, bp["dwm"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
+            else:
+                t = ops.dwconv7(x, bp["dw"], bp["dwb"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
+            ops.convnext_mlp(t.view(-1, C), bp["w1f"], bp["c1"], bp["w2"], bp["b2"], bp["gamma"], x.view(-1, C), 1e-6)
+            return x
         hid = self.buf(tag + ".h", (B, hb, W, 4 * C))
         if self.ln_fold and C % 32 == 0:
             rs = self._row_stats(B * H * W)

@@ -146,6 +146,19 @@ def dwconv7_mma(x, qtab, out=None, work_counter=None):
     return out
 
 
+def convnext_mlp_supported(C):
+    return bool(_L().uc_convnext_mlp_supported(int(C)))
+
+
+def convnext_mlp(t, w1f, c1, w2, b2, gamma, x, eps=1e-6):
+    """x[M,C] += gamma * (W2 . GELU(W1f . LN0(t) + c1) + b2) in one launch (uc_convnext_mlp); t, x: [M, C] bf16 contiguous."""
+    M, C = t.shape
+    assert t.is_contiguous() and x.is_contiguous() and x.shape == t.shape and t.dtype == x.dtype == torch.bfloat16
+    assert w1f.dtype == torch.bfloat16 and w1f.numel() == 4 * C * C and w2.dtype == torch.bfloat16 and w2.numel() == 4 * C * C
+    _lib.check(_L().uc_convnext_mlp(_p(t), _p(w1f), _p(c1), _p(w2), _p(b2), _p(gamma), _p(x), M, C, ctypes.c_float(eps), _S()), "uc_convnext_mlp")
+    return x
+
+
 def stem_ln(img, w48, bias, lnw, lnb, eps=1e-6):
     """img: fp32 NCHW [B,3,H,W] or uint8 NHWC [B,H,W,3] (BGR)."""
     u8 = img.dtype == torch.uint8
