@@ -1,4 +1,4 @@
-"""The GELU of the conv_gemm epilogue: the five coefficients compiled into unicorn_b200/csrc/conv_gemm.cu (gelu2) are read from
+"""The GELU of the conv_gemm epilogue: the five coefficients compiled into unicorn_b200/csrc/uc_epilogue.cuh (gelu2) are read from
 the source and evaluated in fp32 exactly as the kernel does (x * rcp(1 + ex2(x * P(x^2)))); the result must stay within 4e-6 of
 the exact erf GELU over the real line and saturate correctly — the bound DESIGN.md 4.1 states."""
 import os
@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_kernel_gelu_constants_meet_the_stated_bound():
-    src = open(os.path.join(ROOT, "unicorn_b200", "csrc", "conv_gemm.cu")).read()
+    src = open(os.path.join(ROOT, "unicorn_b200", "csrc", "uc_epilogue.cuh")).read()
     body = src[src.index("f32x2 gelu2(f32x2 x)"):]
     c = [np.float32(re.search(rf"c{i} = pk2\(([-+0-9.e]+)f", body).group(1)) for i in range(5)]
     assert abs(float(c[0]) + 1.59565837 * np.log2(np.e)) < 1e-6          # c0 = -log2(e) * first logit coefficient
