@@ -44,7 +44,9 @@ class QDTrackerOracle:
             ids.append(torch.full((bd["embeds"].size(0),), -1, dtype=torch.long))
         return torch.cat(boxes), torch.cat(labels), torch.cat(embeds), torch.cat(ids)
 
-    def match(self, bboxes, labels, track_feats, frame_id):
+    def _filter_and_scores(self, bboxes, labels, track_feats):
+        """:139-170 without touching the state: score-sorted, duplicate-filtered detections and their bi-softmax score matrix
+        against the memo (None when there is nothing to match)."""
         P = self.p
         order = bboxes[:, -1].sort(descending=True)[1]  # :139-142
         bboxes, labels, embeds = bboxes[order], labels[order], track_feats[order]
@@ -55,13 +57,33 @@ class QDTrackerOracle:
             if (ious[i, :i] > thr).any():
                 valid[i] = False
         bboxes, labels, embeds = bboxes[valid], labels[valid], embeds[valid]
-        ids = torch.full((bboxes.size(0),), -1, dtype=torch.long)
+        scores, m_ids = None, None
         if bboxes.size(0) > 0 and self.tracklets:  # :161 (`empty` looks at tracklets only)
             m_boxes, m_labels, m_embeds, m_ids = self._memo()
             feats = embeds @ m_embeds.t()  # :166-170 bi-softmax
             scores = (feats.softmax(dim=1) + feats.softmax(dim=0)) / 2
             if P["cats"]:
                 scores = scores * (labels.view(-1, 1) == m_labels.view(1, -1)).float()
+        return bboxes, labels, embeds, scores, m_ids
+
+    def decision_margin(self, bboxes, labels, track_feats):
+        """(score matrix, smallest distance of a row's decision from flipping): per detection row the lead of its best memo entry over
+        the second best and the distance of the best score from the thresholds it is compared with (:188-199) — what a perturbation
+        of the scores has to exceed to change an id.  (None, inf) when nothing is matched."""
+        P = self.p
+        _, _, _, scores, _ = self._filter_and_scores(bboxes, labels, track_feats)
+        if scores is None or scores.numel() == 0:
+            return None, float("inf")
+        top = scores.topk(min(2, scores.shape[1]), dim=1)[0]
+        lead = top[:, 0] - (top[:, 1] if top.shape[1] > 1 else 0.0)
+        thr = torch.minimum((top[:, 0] - P["match"]).abs(), (top[:, 0] - P["nmsc"]).abs())
+        return scores, float(torch.minimum(lead, thr).min())
+
+    def match(self, bboxes, labels, track_feats, frame_id):
+        P = self.p
+        bboxes, labels, embeds, scores, m_ids = self._filter_and_scores(bboxes, labels, track_feats)
+        ids = torch.full((bboxes.size(0),), -1, dtype=torch.long)
+        if scores is not None:
             for i in range(bboxes.size(0)):  # :188-199 greedy in score order with column zeroing
                 conf, j = torch.max(scores[i], dim=0)
                 tid = m_ids[j]

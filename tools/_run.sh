@@ -1,1 +1,1 @@
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
+timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -6

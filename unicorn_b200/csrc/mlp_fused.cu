@@ -2,8 +2,8 @@
 //
 //     x += gamma * ( W2 . GELU( W1 . LayerNorm(t) + b1 ) + b2 )          t = depthwise-conv output, x = the block's input (shortcut)
 //
-// in ONE persistent launch for the stages whose channel count C fits a shared-memory row tile (C = 96, 192: stage 1 of every
-// backbone, stage 2 of ConvNeXt-T).  There the separate kernels are bound by the 4C hidden map, not by the tensor pipe: at 800x1280 /
+// in ONE persistent launch for the stages whose channel count C fits a shared-memory row tile (C = 96, 192, 384: stages 1-2 of
+// ConvNeXt-L, stages 1-3 of ConvNeXt-T; C = 384 has room for one row-tile buffer and one stage per weight ring only).  There the separate kernels are bound by the 4C hidden map, not by the tensor pipe: at 800x1280 /
 // ConvNeXt-L stage 1 it is 64000 x 768 x 2 B = 98 MB that pwconv1 writes to and pwconv2 reads back from HBM (69 + 40 us for 2 x 19
 // GFLOP), plus a 17 us LayerNorm pass.  Here the hidden activations never leave the SM:
 //
@@ -44,7 +44,11 @@ struct MlpCfg {
   static constexpr int W2_BYTES = C * 128;              // C output rows x 64 hidden (128 B)
   static constexpr int H_BYTES = kMlpRows * 128;        // 128 rows x 64 hidden
   static constexpr int NCHUNK = 4 * C / kMlpHC;
-  static constexpr int SMEM = 2 * (A_BYTES + W1_BYTES + W2_BYTES + H_BYTES) + 1024 + 512;
+  static constexpr int AS = C <= 192 ? 2 : 1;           // row-tile buffers and weight-ring stages: C = 384 only has room for one of each
+  static constexpr int WS = C <= 192 ? 2 : 1;           // (the next weight chunk is then requested when the MMAs reading this one retire)
+  static constexpr int N2S = C > 256 ? 2 : 1;           // GEMM2 is issued as N2S UMMAs of N = C / N2S <= 256 columns
+  static constexpr int N2 = C / N2S;
+  static constexpr int SMEM = AS * A_BYTES + WS * (W1_BYTES + W2_BYTES) + 2 * H_BYTES + 1024 + 512;
   static constexpr int CPT = C / 32;                    // 16-byte chunks of a row per LayerNorm thread (4 threads per row)
 };
 
@@ -68,10 +72,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
   using Cfg = MlpCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                           // [2][KB][128 rows][128 B]
-  uint8_t* sW1 = sA + 2 * Cfg::A_BYTES;         // [2][KB][64 rows][128 B]
-  uint8_t* sW2 = sW1 + 2 * Cfg::W1_BYTES;       // [2][C rows][128 B]
-  uint8_t* sH = sW2 + 2 * Cfg::W2_BYTES;        // [2][128 rows][128 B]
+  uint8_t* sA = smem;                                 // [AS][KB][128 rows][128 B]
+  uint8_t* sW1 = sA + Cfg::AS * Cfg::A_BYTES;         // [WS][KB][64 rows][128 B]
+  uint8_t* sW2 = sW1 + Cfg::WS * Cfg::W1_BYTES;       // [WS][C rows][128 B]
+  uint8_t* sH = sW2 + Cfg::WS * Cfg::W2_BYTES;        // [2][128 rows][128 B]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sH + 2 * Cfg::H_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + MLP_NBARS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,8 +118,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
   if (warp == 0) {
     // ---------------- TMA producer
     auto load_a = [&](int i) {
-      const int ab = i & 1;
-      mbar_wait(&bar[A_EMPTY + ab], ((i >> 1) & 1) ^ 1);
+      const int ab = i % Cfg::AS;
+      mbar_wait(&bar[A_EMPTY + ab], ((i / Cfg::AS) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bar[A_FULL + ab], Cfg::A_BYTES);
 #pragma unroll
@@ -124,27 +128,46 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
       }
       __syncwarp();
     };
-    if (n_local > 0) load_a(0);
-    int g = 0;
-    for (int i = 0; i < n_local; ++i) {
-      for (int j = 0; j < Cfg::NCHUNK; ++j, ++g) {
-        const int s = g & 1, ph = (g >> 1) & 1;
-        mbar_wait(&bar[W1_EMPTY + s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bar[W1_FULL + s], Cfg::W1_BYTES);
+    // weight chunk g: hidden rows (W1) / columns (W2) 64 (g % NCHUNK) .. + 63
+    auto load_w1 = [&](int g) {
+      const int s = g % Cfg::WS, ph = (g / Cfg::WS) & 1, j = g % Cfg::NCHUNK;
+      mbar_wait(&bar[W1_EMPTY + s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar[W1_FULL + s], Cfg::W1_BYTES);
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb)
-            tma_load_2d(sW1 + s * Cfg::W1_BYTES + kb * (kMlpHC * 128), &p.tmW1, &bar[W1_FULL + s], kb * 64, j * kMlpHC);
-        }
-        __syncwarp();
-        mbar_wait(&bar[W2_EMPTY + s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bar[W2_FULL + s], Cfg::W2_BYTES);
-          tma_load_2d(sW2 + s * Cfg::W2_BYTES, &p.tmW2, &bar[W2_FULL + s], j * kMlpHC, 0);
-        }
-        __syncwarp();
-        if (j == 0 && i + 1 < n_local) load_a(i + 1);
+        for (int kb = 0; kb < Cfg::KB; ++kb)
+          tma_load_2d(sW1 + s * Cfg::W1_BYTES + kb * (kMlpHC * 128), &p.tmW1, &bar[W1_FULL + s], kb * 64, j * kMlpHC);
       }
+      __syncwarp();
+    };
+    auto load_w2 = [&](int g) {
+      const int s = g % Cfg::WS, ph = (g / Cfg::WS) & 1, j = g % Cfg::NCHUNK;
+      mbar_wait(&bar[W2_EMPTY + s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar[W2_FULL + s], Cfg::W2_BYTES);
+#pragma unroll
+        for (int nh = 0; nh < Cfg::N2S; ++nh)
+          tma_load_2d(sW2 + s * Cfg::W2_BYTES + nh * (Cfg::N2 * 128), &p.tmW2, &bar[W2_FULL + s], j * kMlpHC, nh * Cfg::N2);
+      }
+      __syncwarp();
+    };
+    const int total = n_local * Cfg::NCHUNK;
+    // one-stage rings: W1 one chunk ahead of W2 (GEMM1 of chunk g+1 is issued before GEMM2 of g, and the ring can only be refilled
+    // when its reader has retired); two-stage rings: in chunk order (measured 5 % faster there than the look-ahead order)
+    if (n_local > 0) {
+      load_a(0);
+      if (Cfg::WS == 1) load_w1(0);
+    }
+    for (int g = 0; g < total; ++g) {
+      if (Cfg::WS == 1) {
+        if (g + 1 < total) load_w1(g + 1);
+      } else {
+        load_w1(g);
+      }
+      load_w2(g);
+      const int i = g / Cfg::NCHUNK, j = g % Cfg::NCHUNK;
+      // the next row tile: into the other buffer right away, or (single buffer) once the last GEMM1 of this tile has read it
+      if (j == (Cfg::AS == 2 ? 0 : Cfg::NCHUNK - 1) && i + 1 < n_local) load_a(i + 1);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: converged warp, one elected lane issues
@@ -153,27 +176,32 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
     const uint32_t acc2 = tmem_base + kMlpAcc2Col;
     auto gemm2 = [&](int gg, bool first, int i) {  // output accumulator += H chunk gg . W2 chunk gg^T
       const int s = gg & 1, ph = (gg >> 1) & 1;
+      const int ws = gg % Cfg::WS, wph = (gg / Cfg::WS) & 1;
       mbar_wait(&bar[H_FULL + s], ph);
-      mbar_wait(&bar[W2_FULL + s], ph);
+      mbar_wait(&bar[W2_FULL + ws], wph);
       if (first) mbar_wait(&bar[ACC2_EMPTY], (i & 1) ^ 1);  // the previous tile's output has been read out
       tc_fence_after();
       if (elect_one()) {
         const uint64_t ad = h_desc0 + static_cast<uint64_t>((s * Cfg::H_BYTES) >> 4);
-        const uint64_t bd = w2_desc0 + static_cast<uint64_t>((s * Cfg::W2_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(acc2, ad + 2 * k, bd + 2 * k, p.idesc2, (first && k == 0) ? 0u : 1u);
+        for (int nh = 0; nh < Cfg::N2S; ++nh) {
+          const uint64_t bd = w2_desc0 + static_cast<uint64_t>((ws * Cfg::W2_BYTES + nh * (Cfg::N2 * 128)) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(acc2 + static_cast<uint32_t>(nh * Cfg::N2), ad + 2 * k, bd + 2 * k, p.idesc2, (first && k == 0) ? 0u : 1u);
+        }
         umma_commit(&bar[H_EMPTY + s]);
-        umma_commit(&bar[W2_EMPTY + s]);
+        umma_commit(&bar[W2_EMPTY + ws]);
       }
       __syncwarp();
     };
     int g = 0;
     for (int i = 0; i < n_local; ++i) {
-      const int ab = i & 1;
-      mbar_wait(&bar[A_READY + ab], (i >> 1) & 1);  // tile loaded AND normalised
+      const int ab = i % Cfg::AS;
+      mbar_wait(&bar[A_READY + ab], (i / Cfg::AS) & 1);  // tile loaded AND normalised
       for (int j = 0; j < Cfg::NCHUNK; ++j, ++g) {
         const int s = g & 1, ph = (g >> 1) & 1;
-        mbar_wait(&bar[W1_FULL + s], ph);
+        const int ws = g % Cfg::WS, wph = (g / Cfg::WS) & 1;
+        mbar_wait(&bar[W1_FULL + ws], wph);
         mbar_wait(&bar[ACC1_EMPTY + s], ph ^ 1);
         tc_fence_after();
         if (elect_one()) {
@@ -181,11 +209,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB; ++kb) {
             const uint64_t ad = a_desc0 + static_cast<uint64_t>((ab * Cfg::A_BYTES + kb * (kMlpRows * 128)) >> 4);
-            const uint64_t bd = w1_desc0 + static_cast<uint64_t>((s * Cfg::W1_BYTES + kb * (kMlpHC * 128)) >> 4);
+            const uint64_t bd = w1_desc0 + static_cast<uint64_t>((ws * Cfg::W1_BYTES + kb * (kMlpHC * 128)) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(acc1, ad + 2 * k, bd + 2 * k, p.idesc1, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bar[W1_EMPTY + s]);
+          umma_commit(&bar[W1_EMPTY + ws]);
           umma_commit(&bar[ACC1_FULL + s]);
           if (j == Cfg::NCHUNK - 1) umma_commit(&bar[A_EMPTY + ab]);
         }
@@ -207,31 +235,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
     // LayerNorm: thread (r, part) = 4 threads per row, adjacent lanes; part handles the 16-byte chunks part * CPT .. + CPT - 1
     const int lt = static_cast<int>(threadIdx.x) - 64, lr = lt >> 2, lp = lt & 3;
     auto layer_norm_tile = [&](int i) {
-      const int ab = i & 1;
-      mbar_wait(&bar[A_FULL + ab], (i >> 1) & 1);
-      uint8_t* a = sA + ab * Cfg::A_BYTES;
-      uint4 v[Cfg::CPT];
-      uint32_t off[Cfg::CPT];
-#pragma unroll
-      for (int c = 0; c < Cfg::CPT; ++c) {
-        const int gc = lp * Cfg::CPT + c;  // chunk of the row: K block gc / 8, 16-byte slot gc % 8 (swizzled with the row)
-        off[c] = static_cast<uint32_t>((gc >> 3) * (kMlpRows * 128) + lr * 128 + (((gc & 7) ^ (lr & 7)) << 4));
-        v[c] = *reinterpret_cast<const uint4*>(a + off[c]);
-      }
+      const int ab = i % Cfg::AS;
+      mbar_wait(&bar[A_FULL + ab], (i / Cfg::AS) & 1);
+      uint8_t* a = sA + ab * Cfg::A_BYTES + lr * 128;
+      // chunk gc of the row: K block gc / 8, 16-byte slot gc % 8 (swizzled with the row)
+      auto chunk_ptr = [&](int c) {
+        const int gc = lp * Cfg::CPT + c;
+        return reinterpret_cast<uint4*>(a + (gc >> 3) * (kMlpRows * 128) + (((gc & 7) ^ (lr & 7)) << 4));
+      };
       float s1 = 0.f;
-#pragma unroll
+#pragma unroll(Cfg::CPT > 6 ? 3 : Cfg::CPT)
       for (int c = 0; c < Cfg::CPT; ++c) {
-        const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s1 += bf16lo(w[e]) + bf16hi(w[e]);
+        const uint4 v = *chunk_ptr(c);
+        s1 += (bf16lo(v.x) + bf16hi(v.x)) + (bf16lo(v.y) + bf16hi(v.y)) + (bf16lo(v.z) + bf16hi(v.z)) + (bf16lo(v.w) + bf16hi(v.w));
       }
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       const float mean = s1 * (1.f / C);
       float s2 = 0.f;
-#pragma unroll
+#pragma unroll(Cfg::CPT > 6 ? 3 : Cfg::CPT)
       for (int c = 0; c < Cfg::CPT; ++c) {
-        const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+        const uint4 v = *chunk_ptr(c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float d0 = bf16lo(w[e]) - mean, d1 = bf16hi(w[e]) - mean;
@@ -242,13 +267,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
       s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
       s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
       const float rstd = rsqrtf(s2 * (1.f / C) + p.ln_eps);
-#pragma unroll
+#pragma unroll(Cfg::CPT > 6 ? 3 : Cfg::CPT)
       for (int c = 0; c < Cfg::CPT; ++c) {
-        const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+        uint4* ptr = chunk_ptr(c);
+        const uint4 v = *ptr;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = pack2_fast((bf16lo(w[e]) - mean) * rstd, (bf16hi(w[e]) - mean) * rstd, false);
-        *reinterpret_cast<uint4*>(a + off[c]) = make_uint4(o[0], o[1], o[2], o[3]);
+        *ptr = make_uint4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
@@ -292,8 +319,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) convnext_mlp_kernel(const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[H_FULL + s]);
         }
-        if (j == Cfg::NCHUNK / 2 - 1 && i + 1 < n_local) layer_norm_tile(i + 1);
+        if (Cfg::AS == 2 && j == Cfg::NCHUNK / 2 - 1 && i + 1 < n_local) layer_norm_tile(i + 1);
       }
+      if (Cfg::AS == 1 && i + 1 < n_local) layer_norm_tile(i + 1);  // single buffer: the producer refilled it after this tile's last GEMM1
       // ---- output: x += gamma * (acc2 + b2)
       const long grow = static_cast<long>(tile_of(i)) * kMlpRows + row;
       const bool valid = grow < p.M;
@@ -363,13 +391,13 @@ static int launch_mlp(MlpParams& p, cudaStream_t stream) {
 
 using namespace uc;
 
-extern "C" int uc_convnext_mlp_supported(int C) { return C == 96 || C == 192; }
+extern "C" int uc_convnext_mlp_supported(int C) { return C == 96 || C == 192 || C == 384; }
 
 extern "C" int uc_convnext_mlp(const void* t_bf16, const void* w1f_bf16, const float* c1, const void* w2_bf16, const float* b2,
                                const float* gamma, void* x_bf16, int M, int C, float ln_eps, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!t_bf16 || !w1f_bf16 || !c1 || !w2_bf16 || !b2 || !gamma || !x_bf16) return set_error(UC_EINVAL, "uc_convnext_mlp: null pointer");
-  if (!uc_convnext_mlp_supported(C)) return set_error(UC_EINVAL, "uc_convnext_mlp: C = %d not supported (96, 192)", C);
+  if (!uc_convnext_mlp_supported(C)) return set_error(UC_EINVAL, "uc_convnext_mlp: C = %d not supported (96, 192, 384)", C);
   if (M < 1) return set_error(UC_EINVAL, "uc_convnext_mlp: empty map");
   if ((reinterpret_cast<uintptr_t>(t_bf16) | reinterpret_cast<uintptr_t>(w1f_bf16) | reinterpret_cast<uintptr_t>(w2_bf16)) & 15 ||
       (reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(gamma)) & 31)
@@ -397,7 +425,7 @@ extern "C" int uc_convnext_mlp(const void* t_bf16, const void* w1f_bf16, const f
   {
     uint64_t dims[2] = {static_cast<uint64_t>(4 * C), static_cast<uint64_t>(C)};
     uint64_t strides[1] = {static_cast<uint64_t>(4 * C) * es};
-    uint32_t box[2] = {kMlpHC, static_cast<uint32_t>(C)};
+    uint32_t box[2] = {kMlpHC, static_cast<uint32_t>(C > 256 ? C / 2 : C)};
     rc = encode_tmap(&p.tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2_bf16, dims, strides, box);
     if (rc) return rc;
   }
@@ -407,6 +435,6 @@ extern "C" int uc_convnext_mlp(const void* t_bf16, const void* w1f_bf16, const f
   p.m_tiles = (M + kMlpRows - 1) / kMlpRows;
   p.ln_eps = ln_eps;
   p.idesc1 = umma_idesc_f16(1u, kMlpRows, kMlpHC);
-  p.idesc2 = umma_idesc_f16(1u, kMlpRows, static_cast<uint32_t>(C));
-  return C == 96 ? launch_mlp<96>(p, stream) : launch_mlp<192>(p, stream);
+  p.idesc2 = umma_idesc_f16(1u, kMlpRows, static_cast<uint32_t>(C > 256 ? C / 2 : C));
+  return C == 96 ? launch_mlp<96>(p, stream) : C == 192 ? launch_mlp<192>(p, stream) : launch_mlp<384>(p, stream);
 }
