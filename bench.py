@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--config", default="unicorn_track_large")
     ap.add_argument("--size", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="frames in flight of the headline measurement (>= 2; the sequential numbers are always reported too)")
+    ap.add_argument("--depth", type=int, default=3, help="frames in flight of the headline measurement (>= 2; the sequential numbers are always reported too)")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] (MOT 1536x2048) and configs[3] (VOS mask) workloads")
     ap.add_argument("--save-tuning", default=None, help="directory: write every engine's per-layer N-tile table (with UC_NO_TUNED=1: fresh autotuning)")
     args = ap.parse_args()
