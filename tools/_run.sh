@@ -1,2 +1,3 @@
-for d in 2 3 4; do python bench.py --steps 30 --warmup 5 --no-extra --depth $d 2>&1 | tail -1 | python -c "
-import json,sys; b=json.loads(sys.stdin.read()); print('depth', b['config'].get('frames_in_flight'), 'value', round(b['value'],1), 'e2e', round(b['e2e']['value'],1), 'seq', round(b['sequential']['value'],1), 'next', b.get('pipelined_%d_frames' % (b['config'].get('frames_in_flight')+1),{}).get('value'))"; done
+for w in 4 8; do echo "UC_DW_MMA_WARPS=$w"; UC_DW_MMA_WARPS=$w timeout 300 python tools/bench_dw.py 2>&1 | sed -e 's/static-schedule.*//' ; done
+UC_DW_MMA_WARPS=8 timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "dwconv_tiled" 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "dwconv_tiled" 2>&1 | tail -2

@@ -30,6 +30,7 @@
 #include "uc_common.h"
 #include "../../include/unicorn_b200.h"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace uc {
 
@@ -41,9 +42,7 @@ constexpr int kMmPlaneBytes = kMmHH * kMmHW * 2;                      // 1056 B 
 constexpr int kMmPlanarBytes = kMmCH * kMmPlaneBytes;                 // 33792
 constexpr int kMmPairBytes = kMmCH * 7 * 8 * 4;                       // 7168: tap pair table of one chunk ...
 constexpr int kMmQBytes = kMmPairBytes + kMmCH * 4;                   // ... + its 32 biases (fp32) = 7296
-constexpr int kMmThreads = 128;
 constexpr int kMmSmem = kMmStageBytes + kMmPlanarBytes + kMmQBytes + 128 + 128;
-constexpr int kMmCtasPerSm = 3;
 
 struct alignas(64) DwMmaParams {
   CUtensorMap tmX;
@@ -67,7 +66,10 @@ struct DwFrag {
   uint32_t q[2];
 };
 
-__global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(const __grid_constant__ DwMmaParams p) {
+// NW = warps per CTA: 4 (8 channels per warp, 3 CTAs / SM; the default) or 8 (4 channels per warp, 2 CTAs / SM; experiments only)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 2) dwconv7_mma_kernel(const __grid_constant__ DwMmaParams p) {
+  constexpr int CPW = kMmCH / NW;  // channels per warp
   extern __shared__ uint8_t dsm_raw[];
   uint8_t* stage = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
   uint8_t* planar = stage + kMmStageBytes;                                           // [32 planes][22][24] bf16
@@ -114,14 +116,15 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
   }
   // ldmatrix row addresses of this lane inside a plane.  x4: {rows 0-7, cols 0-7}, {rows 8-15, cols 0-7}, {rows 0-7, cols 8-15},
   // {rows 8-15, cols 8-15};  x2: {rows 0-7, cols 16-23}, {rows 8-15, cols 16-23} (lanes 0-15 give the addresses)
-  const uint32_t planar_w = smem_u32(planar) + warp * kMmPlaneBytes;  // plane of the warp's channel c = 4 c + warp
+  const int fc = warp * CPW;  // first channel of the warp in the chunk; its channel c lives in plane mm_plane(fc + c) = mm_plane(fc) + 4 c
+  const uint32_t planar_w = smem_u32(planar) + mm_plane(fc) * kMmPlaneBytes;
   const uint32_t lm4 = planar_w + static_cast<uint32_t>((((lane & 7) + ((lane >> 3) & 1) * 8) * kMmHW + (lane >> 4) * 8) * 2);
   const uint32_t lm2 = planar_w + static_cast<uint32_t>(((lane & 15) * kMmHW + 16) * 2);
   // B fragments from the pair table: entry d+1 feeds the first register (d >= -1), entry d+9 the second (d <= -2)
   const int d = 2 * t - g - 1;
   const bool first = d >= -1;
-  const uint32_t q_lane = smem_u32(qs) + static_cast<uint32_t>((warp * 8 * 7 * 8 + (first ? d + 1 : d + 9)) * 4);
-  const float* bias_s = reinterpret_cast<const float*>(qs + kMmPairBytes) + warp * 8;
+  const uint32_t q_lane = smem_u32(qs) + static_cast<uint32_t>((fc * 7 * 8 + (first ? d + 1 : d + 9)) * 4);
+  const float* bias_s = reinterpret_cast<const float*>(qs + kMmPairBytes) + fc;
   // transposition roles: lane = (pixel pair i, channel quarter q); odd i read their two pixels in the other order (no bank conflict
   // between the 128-byte-strided pairs), which only changes the byte-permute selectors
   const int tq = lane & 3, tsw = (lane >> 2) & 1;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
     const int chunk = s_info[(it & 1) * 4 + 0];
     if (chunk < 0) break;
     const int b = s_info[(it & 1) * 4 + 1], oh0 = s_info[(it & 1) * 4 + 2], ow0 = s_info[(it & 1) * 4 + 3];
-    const int c0 = chunk * kMmCH + warp * 8;  // first of this warp's 8 channels
+    const int c0 = chunk * kMmCH + fc;  // first of this warp's CPW channels
     const bool new_chunk = chunk != prev_chunk;
     prev_chunk = chunk;
     if (new_chunk && threadIdx.x == 0) {  // every warp left the previous item's MMA phase (barrier at the end of the loop body)
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
     {
       const uint4* st = reinterpret_cast<const uint4*>(stage);
 #pragma unroll 3
-      for (int pp = warp * 8 + (lane >> 2); pp < kMmHH * kMmHW / 2; pp += 32) {
+      for (int pp = warp * 8 + (lane >> 2); pp < kMmHH * kMmHW / 2; pp += NW * 8) {
         const uint4 va = st[(2 * pp + tsw) * 4 + tq];
         const uint4 vb = st[(2 * pp + (tsw ^ 1)) * 4 + tq];
         const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
@@ -177,11 +180,11 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
       mbar_wait(&bar[1], q_phase);
       q_phase ^= 1;
     }
-    if (c0 < p.C) {  // C % 8 == 0: the warp's 8 channels are in range together
+    if (c0 < p.C) {  // C % 8 == 0: the warp's channels are in range together
       // ---- 4 channel pairs x 7 filter rows; per step and channel: 3 fragment halves, 1 tap pair, 2 MMAs (column blocks 0 and 1)
-      float acc[8][2][4];
+      float acc[CPW][2][4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < CPW; ++c) {
         const float bv = bias_s[c];
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[c][0][e] = acc[c][1][e] = bv;
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
       DwFrag fr[2];
       load_frag(0, fr[0]);
 #pragma unroll
-      for (int s = 0; s < 28; ++s) {
-        if (s + 1 < 28) load_frag(s + 1, fr[(s + 1) & 1]);
+      for (int s = 0; s < CPW / 2 * 7; ++s) {
+        if (s + 1 < CPW / 2 * 7) load_frag(s + 1, fr[(s + 1) & 1]);
         const DwFrag& f = fr[s & 1];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
                          : "r"(f.a[j][2 * nb]), "r"(f.a[j][2 * nb + 1]), "r"(f.a[j][2 * nb + 2]), "r"(f.a[j][2 * nb + 3]), "r"(b0), "r"(b1));
         }
       }
-      // ---- a lane holds 8 consecutive channels of the pixels (g | g+8, 8 nb + 2t | 2t+1): 16-byte stores
+      // ---- a lane holds CPW consecutive channels of the pixels (g | g+8, 8 nb + 2t | 2t+1): 16- / 8-byte stores
       uint16_t* yb = p.y + ((static_cast<size_t>(b) * p.H + oh0) * p.W + ow0) * p.C + c0;
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb)
@@ -211,10 +214,15 @@ __global__ void __launch_bounds__(kMmThreads, kMmCtasPerSm) dwconv7_mma_kernel(c
         for (int e = 0; e < 4; ++e) {
           const int r = g + (e >> 1) * 8, cl = nb * 8 + 2 * t + (e & 1);
           if (oh0 + r < p.H && ow0 + cl < p.W) {
-            uint4 o;
-            o.x = pack_bf16(acc[0][nb][e], acc[1][nb][e]); o.y = pack_bf16(acc[2][nb][e], acc[3][nb][e]);
-            o.z = pack_bf16(acc[4][nb][e], acc[5][nb][e]); o.w = pack_bf16(acc[6][nb][e], acc[7][nb][e]);
-            *reinterpret_cast<uint4*>(yb + (static_cast<size_t>(r) * p.W + cl) * p.C) = o;
+            uint16_t* dst = yb + (static_cast<size_t>(r) * p.W + cl) * p.C;
+            if constexpr (CPW == 8) {
+              uint4 o;
+              o.x = pack_bf16(acc[0][nb][e], acc[1][nb][e]); o.y = pack_bf16(acc[2][nb][e], acc[3][nb][e]);
+              o.z = pack_bf16(acc[4][nb][e], acc[5][nb][e]); o.w = pack_bf16(acc[6][nb][e], acc[7][nb][e]);
+              *reinterpret_cast<uint4*>(dst) = o;
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(acc[0][nb][e], acc[1][nb][e]), pack_bf16(acc[2][nb][e], acc[3][nb][e]));
+            }
           }
         }
     }
@@ -253,15 +261,22 @@ extern "C" int uc_dwconv7_mma(const void* x_bf16, const void* qtab, void* y_bf16
   const long items = static_cast<long>(p.tiles_w) * p.tiles_h * B * ((C + kMmCH - 1) / kMmCH);
   if (items > 0x7fffffffL) return set_error(UC_EINVAL, "uc_dwconv7_mma: too many tiles");
   p.n_items = static_cast<int>(items);
+  // 4 warps per item; the 8-warp variant (UC_DW_MMA_WARPS=8) was measured slower on every backbone stage of ConvNeXt-L at 800x1280 (34.0 /
+  // 20.1 / 14.0 us vs 26.4 / 15.6 / 13.2 on stages 1-3, 8.2 vs 8.6 on stage 4: profiles/r2_dwconv_mma_microbench.txt) and is kept for experiments
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("UC_DW_MMA_WARPS"); forced = e ? atoi(e) : 0; }
+  const bool wide = forced == 8;
   static PerDeviceFlag attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv7_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmSmem);
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv7_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmSmem);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "uc_dwconv7_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  const int grid = static_cast<int>(std::min<long>(items, static_cast<long>(num_sms()) * kMmCtasPerSm));
-  cudaError_t e = launch_pdl(dwconv7_mma_kernel, dim3(grid), dim3(kMmThreads), kMmSmem, stream, p);
+  const int grid = static_cast<int>(std::min<long>(items, static_cast<long>(num_sms()) * (wide ? 2 : 3)));
+  cudaError_t e = wide ? launch_pdl(dwconv7_mma_kernel<8>, dim3(grid), dim3(256), kMmSmem, stream, p)
+                       : launch_pdl(dwconv7_mma_kernel<4>, dim3(grid), dim3(128), kMmSmem, stream, p);
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "uc_dwconv7_mma launch: %s", cudaGetErrorString(e));
   return check_launch("uc_dwconv7_mma");
 }
