@@ -401,7 +401,7 @@ def main():
     t_corr = sorted(ts)[len(ts) // 2]
     # ---------------- dominant kernel: conv_gemm on the two stage-3 pointwise GEMM shapes (54 of the 172 conv launches of
     # a frame, 37 % of its device time), timed the way the frame runs them: kernel nodes of a CUDA graph, CUDA events.
-    conv_roof = None
+    conv_roof = dw_roof = mlp_roof = None
     RI = roofline_inputs()
     if "large" in args.config and (H, W) == (800, 1280):
         xs = torch.randn(1, 50, 80, 768, device=dev).bfloat16()
@@ -439,6 +439,46 @@ def main():
                                "M = 4000 pixels, CUDA-graph nodes",
                      "peak_source": "measured bf16_tflops (burst)"}
 
+        # ---- the two other hand-written hot kernels of a ConvNeXt block on its stage-1 shape: the tensor-core depthwise 7x7 and the fused
+        # LayerNorm + MLP (CUDA-graph nodes, 10 launches per replay; the 49 MB working set stays L2 resident like inside the frame)
+        def graph_time(fn, reps=10):
+            fn()
+            torch.cuda.synchronize()
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gg):
+                for _ in range(reps):
+                    fn()
+            gg.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                gg.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / 1e3 / (3 * reps)
+        M1, C1 = 200 * 320, 192
+        x1 = torch.randn(1, 200, 320, C1, device=dev).bfloat16()
+        y1 = torch.empty_like(x1)
+        qt = ops.pack_dw_weight_mma(torch.randn(C1, 1, 7, 7, device=dev) / 7, torch.randn(C1, device=dev))
+        t_dw = graph_time(lambda: ops.dwconv7_mma(x1, qt, out=y1))
+        dw_bytes = 4.0 * M1 * C1  # read + write the bf16 map once
+        dw_roof = {"bound": "hbm", "achieved": dw_bytes / t_dw / 1e9, "peak": peaks()["hbm"], "unit": "GB/s", "frac": dw_bytes / t_dw / 1e9 / peaks()["hbm"],
+                   "us_per_launch": t_dw * 1e6, "traffic": RI["kernels"].get("r2_ncu_dwmma_s1", {}).get("dram_bytes"),
+                   "kernel": "uc::dwconv7_mma_kernel<4> (depthwise 7x7 as Toeplitz blocks on mma.sync), ConvNeXt-L stage 1: 200x320x192, static item schedule",
+                   "note": "algorithmic bytes (49 MB: the map read and written once) over the launch time; the kernel is bound by shared-memory wavefronts "
+                           "(ldmatrix), not by HBM — DESIGN.md 4.3", "peak_source": "measured hbm_gbs"}
+        w1f = ops.pack_conv_weight(torch.randn(4 * C1, C1, 1, 1, device=dev) / C1 ** 0.5)
+        w2s = ops.pack_conv_weight(torch.randn(C1, 4 * C1, 1, 1, device=dev) / (4 * C1) ** 0.5)
+        c1v, b2v, gmv = torch.randn(4 * C1, device=dev), torch.randn(C1, device=dev), torch.randn(C1, device=dev) * 0.1
+        t_mlp = graph_time(lambda: ops.convnext_mlp(y1.view(-1, C1), w1f, c1v, w2s, b2v, gmv, x1.view(-1, C1)))
+        fl_mlp = 2 * 2.0 * M1 * C1 * 4 * C1
+        mlp_roof = {"bound": "tensor", "achieved": fl_mlp / t_mlp / 1e12, "peak": pk_burst(), "unit": "TFLOP/s", "frac": fl_mlp / t_mlp / 1e12 / pk_burst(),
+                    "us_per_launch": t_mlp * 1e6, "traffic": RI["kernels"].get("r2_ncu_mlp_s1", {}).get("dram_bytes"),
+                    "kernel": "uc::convnext_mlp_kernel<192> (LayerNorm + pwconv1 + GELU + pwconv2 + layer scale + residual), ConvNeXt-L stage 1: M = 64000 pixels",
+                    "note": "the GELU of the 64000 x 768 hidden activations (2 MUFU operations per element, 16 per clock and SM) bounds this kernel at "
+                            "~26 us, not the tensor pipe; the separate kernels it replaces take 120 us (profiles/r2_mlp_fused_microbench.txt)",
+                    "peak_source": "measured bf16_tflops (burst)"}
+
     extra = {} if args.no_extra else extra_workloads(dev, rank, world, max(8, min(K, 24)), sync_all, args.save_tuning if rank == 0 else None)
     if args.save_tuning and rank == 0:
         eng.save_tuning(os.path.join(args.save_tuning, f"{args.config}.json"))
@@ -475,6 +515,7 @@ def main():
                      "kernel": "whole-frame CUDA graph (1997 GFLOP algorithmic per 800x1280 frame, SURVEY §8d)",
                      "peak_source": pk["src"] + " bf16_tflops_sustained"},
         "roofline_conv": conv_roof,
+        "roofline_dwconv": dw_roof, "roofline_mlp": mlp_roof,
         "roofline_corr": {"bound": "tensor", "traffic": RI["kernels"].get("r2_ncu_corr", {}).get("dram_bytes"),
                           "hbm_note": "the fused kernel moves only its algorithmic 8.26 MB (the 16000^2 similarity matrix never leaves the SM), so it is bound "
                                       "by the tensor / MUFU / issue pipes, not by HBM: hbm_frac is reported because BASELINE.json's metric asks for it, it is not a "

@@ -125,7 +125,7 @@ UC_API int uc_dwconv7(const void* x_bf16, const float* w49, const float* bias, v
 UC_API int uc_dwconv7_mma(const void* x_bf16, const void* qtab, void* y_bf16, int B, int H, int W, int C, int* work_counter, void* stream);
 
 /* Fused back half of a ConvNeXt block (unicorn/models/backbone/convnext.py:45-52: norm -> pwconv1 -> GELU -> pwconv2 -> gamma ->
- * residual) in one launch, for C = 96 / 192 (uc_convnext_mlp_supported): x[M][C] += gamma * (W2 . GELU(W1f . LN0(t) + c1) + b2), LN0 =
+ * residual) in one launch, for C = 96 / 192 / 256 / 384 (uc_convnext_mlp_supported): x[M][C] += gamma * (W2 . GELU(W1f . LN0(t) + c1) + b2), LN0 =
  * LayerNorm without affine (eps = ln_eps) over the C channels of a row of t[M][C] (the depthwise-conv output), W1f[4C][C] = pwconv1
  * weight with the LayerNorm weight folded in (W1 diag(g)), c1[4C] = b1 + W1 beta, W2[C][4C].  bf16 maps and weights, fp32 vectors;
  * t / weights 16-byte, x / vectors 32-byte aligned.  The 4C hidden activations stay in shared / tensor memory (csrc/mlp_fused.cu). */

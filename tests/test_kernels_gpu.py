@@ -78,7 +78,7 @@ def test_dwconv_tiled(C, H, W):
     assert torch.equal(om, om2)
 
 
-@pytest.mark.parametrize("C,M", [(192, 128), (192, 1000), (96, 777), (192, 64000), (96, 40000), (384, 100), (384, 16000), (384, 49152)])
+@pytest.mark.parametrize("C,M", [(192, 128), (192, 1000), (96, 777), (192, 64000), (96, 40000), (384, 100), (384, 16000), (384, 49152), (256, 300), (256, 16000)])
 def test_convnext_mlp_fused(C, M):
     """uc_convnext_mlp (LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual in one launch, convnext.py:45-52) against
     the same chain in fp32 torch on the bf16 inputs / weights, and against the unfused kernels of the library."""

@@ -21,7 +21,7 @@ def timed(fn):
     return a.elapsed_time(b) * 1e3 / (2 * R)
 
 
-for name, M, C in [("L.s1 800x1280", 64000, 192), ("L.s1 1536x2048", 196608, 192), ("T.s1 800x1280", 64000, 96), ("T.s2 800x1280", 16000, 192), ("L.s2 800x1280", 16000, 384), ("L.s2 1536x2048", 49152, 384)]:
+for name, M, C in [("L.s1 800x1280", 64000, 192), ("L.s1 1536x2048", 196608, 192), ("T.s1 800x1280", 64000, 96), ("T.s2 800x1280", 16000, 192), ("L.s2 800x1280", 16000, 384), ("L.s2 1536x2048", 49152, 384), ("head.l0 800x1280", 16000, 256), ("head.l1 800x1280", 4000, 256)]:
     t = torch.randn(M, C, device=dev).bfloat16()
     x = torch.randn(M, C, device=dev).bfloat16()
     lw, lb = torch.randn(C, device=dev), torch.randn(C, device=dev)

@@ -2,8 +2,9 @@
 //
 //     x += gamma * ( W2 . GELU( W1 . LayerNorm(t) + b1 ) + b2 )          t = depthwise-conv output, x = the block's input (shortcut)
 //
-// in ONE persistent launch for the stages whose channel count C fits a shared-memory row tile (C = 96, 192, 384: stages 1-2 of
-// ConvNeXt-L, stages 1-3 of ConvNeXt-T; C = 384 has room for one row-tile buffer and one stage per weight ring only).  There the separate kernels are bound by the 4C hidden map, not by the tensor pipe: at 800x1280 /
+// in ONE persistent launch for the stages whose channel count C fits a shared-memory row tile (C = 96, 192, 256, 384: stages 1-2 of
+// ConvNeXt-L, stages 1-3 of ConvNeXt-T, the attention blocks of the head; C = 256 has room for one row-tile buffer, C = 384 for one
+// row-tile buffer and one stage per weight ring only).  There the separate kernels are bound by the 4C hidden map, not by the tensor pipe: at 800x1280 /
 // ConvNeXt-L stage 1 it is 64000 x 768 x 2 B = 98 MB that pwconv1 writes to and pwconv2 reads back from HBM (69 + 40 us for 2 x 19
 // GFLOP), plus a 17 us LayerNorm pass.  Here the hidden activations never leave the SM:
 //
@@ -44,8 +45,8 @@ struct MlpCfg {
   static constexpr int W2_BYTES = C * 128;              // C output rows x 64 hidden (128 B)
   static constexpr int H_BYTES = kMlpRows * 128;        // 128 rows x 64 hidden
   static constexpr int NCHUNK = 4 * C / kMlpHC;
-  static constexpr int AS = C <= 192 ? 2 : 1;           // row-tile buffers and weight-ring stages: C = 384 only has room for one of each
-  static constexpr int WS = C <= 192 ? 2 : 1;           // (the next weight chunk is then requested when the MMAs reading this one retire)
+  static constexpr int AS = C <= 192 ? 2 : 1;           // row-tile buffers and weight-ring stages: C = 256 has room for one row tile,
+  static constexpr int WS = C <= 256 ? 2 : 1;           // C = 384 for one of each (the next weight chunk is then requested when the MMAs reading this one retire)
   static constexpr int N2S = C > 256 ? 2 : 1;           // GEMM2 is issued as N2S UMMAs of N = C / N2S <= 256 columns
   static constexpr int N2 = C / N2S;
   static constexpr int SMEM = AS * A_BYTES + WS * (W1_BYTES + W2_BYTES) + 2 * H_BYTES + 1024 + 512;
@@ -391,13 +392,13 @@ static int launch_mlp(MlpParams& p, cudaStream_t stream) {
 
 using namespace uc;
 
-extern "C" int uc_convnext_mlp_supported(int C) { return C == 96 || C == 192 || C == 384; }
+extern "C" int uc_convnext_mlp_supported(int C) { return C == 96 || C == 192 || C == 256 || C == 384; }
 
 extern "C" int uc_convnext_mlp(const void* t_bf16, const void* w1f_bf16, const float* c1, const void* w2_bf16, const float* b2,
                                const float* gamma, void* x_bf16, int M, int C, float ln_eps, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!t_bf16 || !w1f_bf16 || !c1 || !w2_bf16 || !b2 || !gamma || !x_bf16) return set_error(UC_EINVAL, "uc_convnext_mlp: null pointer");
-  if (!uc_convnext_mlp_supported(C)) return set_error(UC_EINVAL, "uc_convnext_mlp: C = %d not supported (96, 192, 384)", C);
+  if (!uc_convnext_mlp_supported(C)) return set_error(UC_EINVAL, "uc_convnext_mlp: C = %d not supported (96, 192, 256, 384)", C);
   if (M < 1) return set_error(UC_EINVAL, "uc_convnext_mlp: empty map");
   if ((reinterpret_cast<uintptr_t>(t_bf16) | reinterpret_cast<uintptr_t>(w1f_bf16) | reinterpret_cast<uintptr_t>(w2_bf16)) & 15 ||
       (reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(gamma)) & 31)
@@ -436,5 +437,5 @@ extern "C" int uc_convnext_mlp(const void* t_bf16, const void* w1f_bf16, const f
   p.ln_eps = ln_eps;
   p.idesc1 = umma_idesc_f16(1u, kMlpRows, kMlpHC);
   p.idesc2 = umma_idesc_f16(1u, kMlpRows, static_cast<uint32_t>(C > 256 ? C / 2 : C));
-  return C == 96 ? launch_mlp<96>(p, stream) : C == 192 ? launch_mlp<192>(p, stream) : launch_mlp<384>(p, stream);
+  return C == 96 ? launch_mlp<96>(p, stream) : C == 192 ? launch_mlp<192>(p, stream) : C == 256 ? launch_mlp<256>(p, stream) : launch_mlp<384>(p, stream);
 }

@@ -57,7 +57,7 @@ class UnicornEngine:
         self.ln_fold = bool(int(os.environ.get("UC_LN_FOLD", "0"))) if ln_fold is None else bool(ln_fold)
         # depthwise 7x7 on tensor cores (csrc/dwconv_mma.cu; taps rounded to bf16) instead of the fp32-FMA kernel (csrc/dwconv_tma.cu)
         self.dw_mma = bool(int(os.environ.get("UC_DW_MMA", "1")))
-        # LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual of the blocks with C = 96 / 192 in one launch (csrc/mlp_fused.cu)
+        # LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual of the blocks with C = 96 / 192 / 256 / 384 in one launch (csrc/mlp_fused.cu)
         self.mlp_fused = bool(int(os.environ.get("UC_MLP_FUSED", "1")))
         self._row_arena, self._row_used = None, 0
         self._ctr_arena, self._ctr_used = None, 0  # work counters of the dynamically scheduled kernels (zeroed by begin_frame)
@@ -328,7 +328,9 @@ class UnicornEngine:
             while H % nb:
                 nb += 1
         hb = H // nb
-        if bp.get("fused"):
+        # fused back half (csrc/mlp_fused.cu): one CTA per 128 rows, so only where the map gives the SMs enough row tiles (the head's
+        # C = 256 blocks run it on the stride-8 level only; the backbone stages always, which also keeps the small test configs on it)
+        if bp.get("fused") and (C != 256 or B * H * W >= 12288):
             if self.dw_mma:
                 t = ops.dwconv7_mma(x, bp["dwm"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
             else:
