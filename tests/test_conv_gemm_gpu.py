@@ -91,3 +91,26 @@ def test_conv(case):
         st = gn_stats.double() / 2 ** 22
         assert torch.allclose(st[..., 0].float(), s1, rtol=2e-3, atol=2e-1), (st[..., 0], s1)
         assert torch.allclose(st[..., 1].float(), s2, rtol=2e-3, atol=2e-1), (st[..., 1], s2)
+
+
+def test_gelu_epilogue_whole_range():
+    """The GELU of the epilogue (uc_epilogue.cuh: x * sigmoid(x * P(x^2)) on packed fp32 pairs) over the whole range a pre-activation can
+    take, including values whose exponentials saturate or overflow: a 1x1 conv with the identity as weight and the test values as
+    bias.  fp32 output against torch's exact GELU."""
+    from unicorn_b200 import ops
+    C = 64
+    vals = torch.cat([torch.linspace(-12, 12, 4001), torch.tensor([-1e4, -300.0, -88.0, -40.0, -20.0, 0.0, -0.0, 20.0, 88.0, 300.0, 1e4, 3e38, -3e38])])
+    n = vals.numel()
+    rows = -(-n // C)
+    b = torch.zeros(rows * C)
+    b[:n] = vals
+    x = torch.zeros(1, 1, rows, C, device="cuda", dtype=torch.bfloat16)
+    w = ops.pack_conv_weight(torch.eye(C, device="cuda").view(C, C, 1, 1))
+    got = torch.cat([ops.conv2d(x[:, :, r:r + 1].contiguous(), w, 1, 1, bias=b[r * C:(r + 1) * C].cuda().contiguous(), act=ops.ACT_GELU,
+                                out_dtype=torch.float32).view(-1) for r in range(rows)])[:n].cpu()
+    ref = F.gelu(vals.double()).float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    assert (err <= 1e-5 + 1e-5 * ref.abs()).all(), (err.max(), vals[err.argmax()])
+    # saturation: exactly zero far on the negative side, the identity far on the positive side
+    assert got[vals == -1e4].abs().max() == 0 and abs(got[(vals - 12).abs().argmin()] - 12.0) < 1e-4
