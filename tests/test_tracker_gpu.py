@@ -149,6 +149,43 @@ def test_mot_pipelined_graph_matches_sequential():
         assert torch.equal(r[1], g[1]) and torch.equal(r[0], g[0]), f"frame {t}: tracks differ"
 
 
+def test_mot_byte_arm_three_frames_in_flight_matches_one_stream():
+    """ByteTrack arm (mot_evaluator.py:177-209): with depth=3 the device halves of three frames run on their own streams / engine
+    contexts (CUDA graphs from a context's second frame on); the detection rows handed to BYTETracker.update per frame must be
+    bit-identical to the one-stream driver's, in frame order (the tracker itself is checked in test_byte_tracker_matches_reference_logic)."""
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.mot import UnicornMOTTracker
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.weights import make_state_dict
+
+    class Recorder:  # stands in for BYTETracker: update(dets [n,7] numpy, img_info, img_size)
+        def __init__(self):
+            self.rows = []
+
+        def update(self, dets, img_info, img_size):
+            self.rows.append(torch.from_numpy(dets).clone())
+            return []
+    name = "unicorn_track_tiny"
+    eng = UnicornEngine(make_state_dict(name, 0), name)
+    frames, _ = make_video(10, 320, 320, seed=4, n_obj=3)
+    u8 = frames.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    ref, got = Recorder(), Recorder()
+    seq = UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7, assoc="byte", tracker=ref)
+    for t in range(10):
+        seq.step_tensor(u8[t:t + 1], img_info=(320, 320))
+    pipe = UnicornMOTTracker(eng, (320, 320), conf=0.01, nms=0.7, assoc="byte", tracker=got, use_graph=True, depth=3)
+    sub = 0
+    for t in range(10):
+        while sub < 10 and sub - t < 3:
+            pipe.submit(u8[sub:sub + 1].pin_memory())
+            sub += 1
+        pipe.collect((320, 320))
+    assert all(c.graph is not None for c in pipe._ctxs)
+    assert len(ref.rows) == len(got.rows) == 10 and sum(r.shape[0] for r in ref.rows) > 10
+    for t, (r, g) in enumerate(zip(ref.rows, got.rows)):
+        assert r.shape == g.shape and torch.equal(r, g), f"frame {t}"
+
+
 def test_byte_tracker_matches_reference_logic():
     """30 frames of seeded detections through BYTETracker.update vs the reference's own update() flow
     (tests/golden/byte_tracker.npz: reference STrack/Kalman/association code with lap/cython_bbox emulated)."""

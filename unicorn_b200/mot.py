@@ -13,7 +13,11 @@ is split in a device half and a host half:
 
 Nothing on the device depends on the association (the previous frame's s16 feature is the only carried state), so
 `submit(t+1); collect(t)` overlaps the host association of frame t with the device work of frame t+1 — same results as
-the sequential `step_tensor`, throughput max(device, host) instead of their sum."""
+the sequential `step_tensor`, throughput max(device, host) instead of their sum.
+
+With `assoc="byte"` the frames do not even share the s16 feature: `depth` > 1 keeps that many frames in flight ON THE DEVICE, each on
+its own stream and engine context (UnicornEngine.fork(): same weights, own activations) like UnicornSOTTrack(depth=...); the detections
+are identical to the one-stream driver's (tests/test_mot_gpu.py), collect() still returns them in frame order."""
 import torch
 
 from . import ops
@@ -21,10 +25,26 @@ from .engine import UnicornEngine
 from .tracker import QuasiDenseEmbedTracker
 
 
+class _Ctx:
+    """One frame in flight of the ByteTrack arm: engine context, stream, input buffers, NMS workspace, pinned result slot, graph."""
+
+    def __init__(self, eng, H, W, A, max_dets):
+        dev = eng.dev
+        self.eng, self.stream = eng, torch.cuda.Stream(device=dev)
+        self.ws = ops.PostWorkspace(A, dev)
+        self.img_in = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+        self.img_in_u8 = torch.empty(1, H, W, 3, dtype=torch.uint8, device=dev)
+        self.u8 = False
+        self.slot = dict(cnt=torch.zeros(1, dtype=torch.int32).pin_memory(), dets=torch.zeros(max_dets, 7).pin_memory(),
+                         ev=torch.cuda.Event(), scale=1.0, frame_id=0)
+        self.graph, self.uses, self.last = None, 0, {}
+
+
 class UnicornMOTTracker:
     def __init__(self, engine: UnicornEngine, input_size, conf=0.01, nms=0.7, score_thr=0.1, max_dets=1024, tracker=None,
-                 assoc="qd", use_graph=False):
+                 assoc="qd", use_graph=False, depth=1):
         assert assoc in ("qd", "byte")
+        assert depth == 1 or assoc == "byte", "only the ByteTrack arm has independent frames (the QD arm carries the previous s16 feature)"
         self.eng, self.input_size = engine, tuple(input_size)
         self.conf, self.nms, self.score_thr, self.max_dets = conf, nms, score_thr, max_dets
         self.assoc = assoc
@@ -52,6 +72,8 @@ class UnicornMOTTracker:
         self.use_graph = use_graph
         self._graphs = {}
         self.last = {}
+        self.depth = depth
+        self._ctxs = [_Ctx(engine if i == 0 else engine.fork(), H, W, A, max_dets) for i in range(depth)] if depth > 1 else None
 
     # ------------------------------------------------------------------------------------------ device half
     def _device_frame(self, parity):
@@ -73,9 +95,46 @@ class UnicornMOTTracker:
             self._has_prev.bitwise_or_((cnt > 0).to(torch.int32))
         self.last = dict(embed=emb, head=out)
 
+    def _ctx_frame(self, c):
+        e = c.eng
+        e.begin_frame()
+        fpn, _ = e.backbone(c.img_in_u8 if c.u8 else c.img_in, tag="mot")
+        out = e.head(fpn, None, "mot")
+        ops.postprocess_device(out[0], e.ncls, self.conf, self.nms, c.ws)
+        c.last = dict(embed=None, head=out)
+
+    def _submit_ctx(self, frame, scale):
+        assert self.frame_id - self.collected < self.depth, "collect() a frame first"
+        c = self._ctxs[self.frame_id % self.depth]
+        self.frame_id += 1
+        c.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(c.stream):
+            u8 = frame.dtype == torch.uint8
+            if u8 != c.u8:
+                c.u8, c.graph, c.uses = u8, None, 0
+            (c.img_in_u8 if u8 else c.img_in).copy_(frame, non_blocking=True)
+            c.uses += 1
+            if self.use_graph and c.uses > 1:  # a context's first frame runs eagerly (plan-time autotuning, buffer allocation)
+                if c.graph is None:
+                    torch.cuda.synchronize()
+                    c.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(c.graph, stream=c.stream):
+                        self._ctx_frame(c)
+                c.graph.replay()
+            else:
+                self._ctx_frame(c)
+            s = c.slot
+            s["cnt"].copy_(c.ws.count.view(-1)[:1], non_blocking=True)
+            s["dets"].copy_(c.ws.dets[:self.max_dets], non_blocking=True)
+            s["scale"], s["frame_id"] = scale, self.frame_id
+            s["ev"].record()
+        self.last = c.last
+
     def submit(self, frame, scale=1.0):
         """frame: preprocessed fp32 [1,3,H,W] or uint8 [1,H,W,3] (4x fewer H2D bytes; the float conversion happens in the stem
         kernel), host or device.  Enqueues the frame; returns immediately."""
+        if self._ctxs is not None:
+            return self._submit_ctx(frame, scale)
         assert self.frame_id - self.collected < 2, "collect() the previous frame first"
         self.frame_id += 1
         parity = self.frame_id & 1
@@ -113,7 +172,7 @@ class UnicornMOTTracker:
         ByteTrack: the list of active STracks (img_info = (height, width) of the original image)."""
         assert self.collected < self.frame_id, "nothing submitted"
         self.collected += 1
-        s = self._slots[self.collected & 1]
+        s = self._slots[self.collected & 1] if self._ctxs is None else self._ctxs[(self.collected - 1) % self.depth].slot
         s["ev"].synchronize()
         total = int(s["cnt"][0])
         if total > self.max_dets and not self._warned:
