@@ -178,3 +178,59 @@ def test_vos_graph_replay_matches_eager():
     for a, b in zip(segs_e, segs_g):
         assert np.array_equal(a, b)
     assert st_e == st_g
+
+
+def test_vos_three_frames_in_flight_match_sequential():
+    """submit / collect with depth=3 (worker drivers on engine forks, own streams, CUDA graphs): label maps, soft masks and detection
+    rows of every frame are bit-identical to the synchronous driver's; a frame that adds an object drains the pipeline and the
+    workers pick the new reference group up."""
+    from unicorn_b200.engine import UnicornEngine
+    from unicorn_b200.synthetic import make_video
+    from unicorn_b200.vos import UnicornVOSTrack
+    from unicorn_b200.weights import make_state_dict
+    name = "unicorn_track_tiny_mask"
+    eng = UnicornEngine(make_state_dict(name, 0), name)
+    frames, boxes = make_video(12, 320, 320, seed=9, n_obj=3)
+    u8 = frames.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    lab = torch.zeros(320, 320, dtype=torch.uint8)
+    x1, y1, x2, y2 = boxes[6, 2].int().tolist()
+    lab[y1:y2, x1:x2] = 3
+
+    def run(depth):
+        trk = UnicornVOSTrack(eng, (320, 320), use_graph=True, depth=depth)
+        trk.initialize_tensor(u8[0:1], {1: boxes[0, 0], 2: boxes[0, 1]})
+        out = []
+
+        def keep(o):
+            out.append((o["segmentation"].cpu().clone(), o["soft"].cpu().clone(), {k: (None if v[0] is None else v[0].clone()) for k, v in o["objects"].items()}))
+        order = list(range(1, 6))
+        if depth == 1:
+            for t in order:
+                keep(trk.track_tensor(u8[t:t + 1]))
+        else:
+            sub = 0
+            for k in range(len(order)):
+                while sub < len(order) and sub - k < depth:
+                    trk.submit(u8[order[sub]:order[sub] + 1].pin_memory())
+                    sub += 1
+                keep(trk.collect())
+        keep(trk.track_tensor(u8[6:7], {3: boxes[6, 2]}, lab))  # object 3 appears: synchronous path, pipeline drained
+        order = list(range(7, 12))
+        if depth == 1:
+            for t in order:
+                keep(trk.track_tensor(u8[t:t + 1]))
+        else:
+            sub = 0
+            for k in range(len(order)):
+                while sub < len(order) and sub - k < depth:
+                    trk.submit(u8[order[sub]:order[sub] + 1].pin_memory())
+                    sub += 1
+                keep(trk.collect())
+        return out
+    ref, got = run(1), run(3)
+    assert len(ref) == len(got) == 11 and got[-1][1].shape[0] == 3
+    for t, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r[0], g[0]) and torch.equal(r[1], g[1]), f"frame {t}"
+        assert r[2].keys() == g[2].keys()
+        for k in r[2]:
+            assert (r[2][k] is None) == (g[2][k] is None) and (r[2][k] is None or torch.equal(r[2][k], g[2][k])), (t, k)

@@ -8,6 +8,10 @@ inside the head for every object); per reference group ONE fused correlation lau
 objects (the 16000^2 similarity matrix never exists); the resize to the original frame, the float32 background product and the
 argmax run in one kernel on the device (uc_vos_aggregate); the only per-frame host traffic is the frame in, the label map and the
 detection rows out.  With use_graph=True the steady-state frame is one CUDA-graph replay (re-captured when objects are added).
+
+depth > 1: like in SOT, a frame depends only on the reference frames of its objects, never on the previous frame's result, so
+`submit(frame)` / `collect()` keep `depth` steady-state frames in flight, each on its own stream and engine context (worker drivers
+on UnicornEngine.fork() that share the reference groups); frames that add objects go through track_tensor() with the pipeline drained.
 """
 import ctypes
 
@@ -26,8 +30,9 @@ class _Group:
 
 
 class UnicornVOSTrack:
-    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=1, d_rate=2, use_graph=False):
+    def __init__(self, engine: UnicornEngine, input_size, conf=0.001, nms=0.65, max_inst=1, d_rate=2, use_graph=False, depth=1):
         assert engine.cfg["mask"], "VOS needs a *_mask model"
+        assert depth >= 1
         self.eng, self.input_size = engine, tuple(input_size)
         self.conf, self.nms, self.max_inst, self.d_rate = conf, nms, max_inst, d_rate
         self.num_classes = 1
@@ -48,6 +53,14 @@ class UnicornVOSTrack:
         self.launches_per_frame = 0
         self.debug = False  # tests: keep per-object copies of the head output and the controller maps
         self.last = {}
+        self._rows_host, self._rows_ev, self._pending = None, torch.cuda.Event(), None
+        # frames in flight: worker 0 is this driver, the others are drivers on engine forks sharing groups / geometry
+        self.depth = depth
+        self._stream = torch.cuda.Stream(device=dev) if depth > 1 else None
+        self._workers = [self] + [UnicornVOSTrack(engine.fork(), input_size, conf, nms, max_inst, d_rate, use_graph, depth=1) for _ in range(depth - 1)]
+        for w in self._workers[1:]:
+            w._stream = torch.cuda.Stream(device=dev)
+        self._submitted = self._collected = 0
 
     # ------------------------------------------------------------------------------------------ helpers
     def _stage_input(self, frame):
@@ -88,8 +101,9 @@ class UnicornVOSTrack:
         self.groups = [_Group(ref_feat, e.project_ref(ref_feat), ids, self._label_maps([boxes_xyxy[o] for o in ids]))]
         self.orig_size = tuple(orig_size) if orig_size is not None else self.input_size
         self.r = float(r)
-        self._graph = None
-        self.frame_id = 0
+        for w in self._workers:
+            w._graph, w.frame_id, w._pending = None, 0, None
+        self._submitted = self._collected = 0
         torch.cuda.synchronize()
 
     def _device_frame(self):
@@ -152,19 +166,13 @@ class UnicornVOSTrack:
                                                ctypes.c_void_p(self._seg.data_ptr()), _lib.stream_ptr()), "uc_vos_aggregate")
         return self._seg, self._soft[:n]
 
-    def track_tensor(self, cur_frame, new_boxes_xyxy=None, init_mask=None):
-        """cur_frame: preprocessed frame (fp32 NCHW or uint8 NHWC).  new_boxes_xyxy: dict obj_id -> box (resized-image coordinates)
-        of objects that first appear in this frame, init_mask: their uint8 label map [H0,W0] (unicorn_vos.py:86-98).
-        Returns dict(segmentation=uint8 [H0,W0] device tensor, soft=fp32 [n,H0,W0], objects={obj_id: (det_row [7] cpu | None,
-        mask fp32 [H,W] device at network resolution | None)})."""
+    def _enqueue(self, cur_frame, new_ids=(), new_boxes_xyxy=None, init_mask=None):
+        """Device half of a frame on the current stream + the asynchronous read of the detection rows; no host synchronisation
+        unless a graph has to be (re)captured."""
         e = self.eng
         self.frame_id += 1
         self._stage_input(cur_frame)
         key = tuple(len(g.obj_ids) for g in self.groups)
-        new_ids = list(new_boxes_xyxy.keys()) if new_boxes_xyxy else []
-        if new_ids:
-            assert init_mask is not None and init_mask.dtype == torch.uint8 and tuple(init_mask.shape) == self.orig_size
-            init_mask = init_mask.to(e.dev).contiguous()
         if self.use_graph and not new_ids and self.frame_id > 1:
             if self._graph is None or self._graph_key != key:
                 self._device_frame()  # warm-up: buffers, kernel attributes, plan-time autotuning
@@ -172,7 +180,7 @@ class UnicornVOSTrack:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 l0 = _lib.LAUNCHES
-                with torch.cuda.graph(g):
+                with (torch.cuda.graph(g) if self._stream is None else torch.cuda.graph(g, stream=self._stream)):
                     self._device_frame()
                     self._aggregate()
                 self.launches_per_frame = _lib.LAUNCHES - l0
@@ -188,12 +196,58 @@ class UnicornVOSTrack:
                 self.groups.append(_Group(ref_feat, e.project_ref(ref_feat), new_ids, self._label_maps([new_boxes_xyxy[o] for o in new_ids])))
                 self._graph = None
         n_old = len(self.last["per_obj"])
-        rows = torch.stack(self._det_bufs[:n_old]).cpu() if n_old else torch.zeros(0, 8)  # one D2H read: detection rows + counts
+        if n_old:  # one D2H read: detection rows + counts, into pinned memory
+            if self._rows_host is None or self._rows_host.shape[0] < n_old:
+                self._rows_host = torch.zeros(max(n_old, 4), 8).pin_memory()
+            self._rows_host[:n_old].copy_(torch.stack(self._det_bufs[:n_old]), non_blocking=True)
+        self._rows_ev.record()
+        self._pending = (seg, soft, n_old, bool(new_ids))
+
+    def _finish(self):
+        seg, soft, n_old, had_new = self._pending
+        self._pending = None
+        self._rows_ev.synchronize()
+        rows = self._rows_host[:n_old].clone() if n_old else torch.zeros(0, 8)
         objects = {}
         for oid, po in self.last["per_obj"].items():
             row = rows[po["slot"]]
             objects[oid] = (row[:7].clone(), self._mask_bufs[po["slot"]][0]) if row[7] > 0 else (None, None)
-        return dict(segmentation=seg, soft=soft, objects=objects, ids=self.obj_ids if not new_ids else self.obj_ids)
+        return dict(segmentation=seg, soft=soft, objects=objects, ids=self.obj_ids)
+
+    def track_tensor(self, cur_frame, new_boxes_xyxy=None, init_mask=None):
+        """cur_frame: preprocessed frame (fp32 NCHW or uint8 NHWC).  new_boxes_xyxy: dict obj_id -> box (resized-image coordinates)
+        of objects that first appear in this frame, init_mask: their uint8 label map [H0,W0] (unicorn_vos.py:86-98).
+        Returns dict(segmentation=uint8 [H0,W0] device tensor, soft=fp32 [n,H0,W0], objects={obj_id: (det_row [7] cpu | None,
+        mask fp32 [H,W] device at network resolution | None)})."""
+        assert self._submitted == self._collected, "collect() the frames in flight first"
+        new_ids = list(new_boxes_xyxy.keys()) if new_boxes_xyxy else []
+        if new_ids:
+            assert init_mask is not None and init_mask.dtype == torch.uint8 and tuple(init_mask.shape) == self.orig_size
+            init_mask = init_mask.to(self.eng.dev).contiguous()
+        self._enqueue(cur_frame, new_ids, new_boxes_xyxy, init_mask)
+        return self._finish()
+
+    # ------------------------------------------------------------------------------------------ frames in flight
+    def submit(self, cur_frame):
+        """Enqueue a steady-state frame (no new objects) on the next worker's stream; at most `depth` frames may be uncollected.
+        The tensors of a collected result stay valid until that worker's next submit (`depth` submits later)."""
+        assert self._submitted - self._collected < self.depth, "collect() a frame first"
+        w = self._workers[self._submitted % self.depth]
+        self._submitted += 1
+        if w is not self:  # shared reference state and geometry
+            w.groups, w.orig_size, w.r = self.groups, self.orig_size, self.r
+        if w._stream is None:
+            return w._enqueue(cur_frame)
+        w._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(w._stream):
+            w._enqueue(cur_frame)
+
+    def collect(self):
+        """Result of the oldest submitted frame (same dict as track_tensor)."""
+        assert self._collected < self._submitted, "nothing submitted"
+        w = self._workers[self._collected % self.depth]
+        self._collected += 1
+        return w._finish()
 
     # ------------------------------------------------------------------------------------------ reference protocol
     def initialize(self, image, info: dict):
