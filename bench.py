@@ -224,7 +224,29 @@ def extra_workloads(dev, rank, world, K, sync_all, save_tuning=None):
                                 workload=f"{cfg} MOT detector (mode whole, 64512 anchors) + ByteTrack association of 100 synthetic objects per frame, "
                                          f"1536x2048 (BASELINE configs[2]); device half = CUDA graph, {MD} frames in flight on their own streams, association of frame t overlapped with them",
                                 h2d_bytes_per_step=int(host[0].numel()), d2h_bytes_per_step=int(trk.max_dets * 7 * 4 + 4))
-    del trk, eng
+    del trk
+    # the reference's own association arm (mot_evaluator.py:1005-1057): interaction with the previous frame, embedding upsample, sampling,
+    # QuasiDenseEmbedTracker — the s16 feature of frame t-1 is carried, so the device halves run on one stream (host half overlapped)
+    from unicorn_b200.tracker import QuasiDenseEmbedTracker
+    trq = UnicornMOTTracker(eng, (H, W), tracker=QuasiDenseEmbedTracker(device=dev), use_graph=True)
+    trq.submit(host[0])
+
+    def qd_step(i):
+        trq.submit(host[(i + 1) % 4])
+        trq.collect()
+
+    def qd_replay(i):
+        trq.img_in_u8.copy_(devf[i % 4], non_blocking=True)
+        trq._graphs[i & 1][0].replay()
+    for i in range(4):
+        qd_step(i)  # frames 1-2 eager, 3-4 capture the two parity graphs
+    dt_dev, dt_e2e = timed(qd_replay, qd_step, K)
+    trq.collect()
+    out["mot_1536x2048_qd"] = dict(_frames=K, _dt_dev=dt_dev, _dt_e2e=dt_e2e, gflop_per_frame=(1887.7 + 43.8) * 3.072,  # + interaction and embedding branch of the SOT frame count (1997 - 1887.7 - 65.5 correlation)
+                                   workload=f"{cfg} MOT detector + interaction with the previous frame + embedding + QuasiDense association (the reference's arm), "
+                                            "1536x2048; device half = CUDA graph on one stream (frame t needs the s16 feature of t-1), association overlapped",
+                                   h2d_bytes_per_step=int(host[0].numel()), d2h_bytes_per_step=int(trq.max_dets * (7 + 128) * 4 + 4))
+    del trq, eng
     # ---------------- configs[3]: VOS with the CondInst mask head, 800x1280
     H, W = 800, 1280
     cfg = "unicorn_track_large_mask"
