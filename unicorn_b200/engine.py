@@ -59,6 +59,7 @@ class UnicornEngine:
         self.dw_mma = bool(int(os.environ.get("UC_DW_MMA", "1")))
         # LayerNorm -> pwconv1 -> GELU -> pwconv2 -> layer scale -> residual of the blocks with C = 96 / 192 / 256 / 384 in one launch (csrc/mlp_fused.cu)
         self.mlp_fused = bool(int(os.environ.get("UC_MLP_FUSED", "1")))
+        self.mlp_min_rows = int(os.environ.get("UC_MLP_MIN_ROWS", "0"))  # head (C = 256) blocks: fused on maps with at least this many pixels (see convnext_block)
         self._row_arena, self._row_used = None, 0
         self._ctr_arena, self._ctr_used = None, 0  # work counters of the dynamically scheduled kernels (zeroed by begin_frame)
         self.autotune = autotune
@@ -202,6 +203,12 @@ class UnicornEngine:
             kw2["gn_stats"] = torch.zeros(out.shape[0], gn, 2, dtype=torch.int64, device=self.dev)
         best, best_t, times = 0, None, []
         reps = 6
+        # objective: launch time discounted by the share of the SMs the launch occupies, t * (w + (1 - w) * min(CTAs, 148) / 148) with
+        # w = UC_TUNE_SMTIME_W (default 0.5; 1 = pure latency): with several frames in flight a launch on fewer CTAs leaves SMs to the other
+        # frames' kernels.  Measured on the SOT frame (profiles/r2_autotune_objective.txt): w = 1: 288 frames/s pipelined / 224 sequential,
+        # w = 0.5: 299 / 225, w = 0: 307 / 216 — 0.5 is the largest gain that costs no latency
+        w_lat = float(os.environ.get("UC_TUNE_SMTIME_W", "0.5"))
+        m_tiles = -(-(out.shape[0] * out.shape[1] * out.shape[2]) // 128)
         for bn in cands:
             # timed as the frame runs it: back-to-back kernel nodes of a CUDA graph (stream launches of ~20 us kernels
             # measure launch cadence, not the kernel)
@@ -224,6 +231,9 @@ class UnicornEngine:
             except ops._lib.UnicornB200Error:
                 continue
             times.append((bn, round(t * 1e3, 1)))  # us per launch
+            if w_lat < 1.0 and bn:
+                ctas = m_tiles * -(-Cout // (bn % 1000))
+                t = t * (w_lat + (1.0 - w_lat) * min(ctas, 148) / 148.0)
             if best_t is None or t < best_t * 0.97:  # require a 3 % win to leave the earlier (heuristic-first) choice
                 best, best_t = bn, t
         if os.environ.get("UC_TUNE_LOG"):
@@ -328,9 +338,10 @@ class UnicornEngine:
             while H % nb:
                 nb += 1
         hb = H // nb
-        # fused back half (csrc/mlp_fused.cu): one CTA per 128 rows, so only where the map gives the SMs enough row tiles (the head's
-        # C = 256 blocks run it on the stride-8 level only; the backbone stages always, which also keeps the small test configs on it)
-        if bp.get("fused") and (C != 256 or B * H * W >= 12288):
+        # fused back half (csrc/mlp_fused.cu): one CTA per 128 rows.  On the head's small levels (32 and 8 row tiles at 800x1280) the launch
+        # is slower than the three separate kernels in isolation (31 vs 22 us) but occupies a fifth of their SM-time, and the levels run on
+        # parallel streams next to two more frames in flight: fusing them too is +1.8 % frames/s (286 vs 281), so there is no size gate by default
+        if bp.get("fused") and (C != 256 or B * H * W >= self.mlp_min_rows):
             if self.dw_mma:
                 t = ops.dwconv7_mma(x, bp["dwm"], out=self.buf(tag + ".t", x.shape), work_counter=self._ctr())
             else:
